@@ -1,0 +1,483 @@
+// gb25_api.cu — the C ABI of libgb25cuda (include/gb25cuda.h): handle, device memory, parent-shaped
+// transfers, and the stage sequencing of the Oceananigans HydrostaticFreeSurfaceModel time step
+// (QuasiAdamsBashforth2; SURVEY.md A.4, stage order /root/reference/src/precompile.jl:31-42).
+// There is no CPU path: without a CUDA device gb25_create fails with GB25_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "gb25_internal.h"
+
+static thread_local std::string g_create_error;
+
+#define CK(h, call)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) {                                                                          \
+      char buf_[512];                                                                                 \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      (h)->err = buf_; (h)->sticky = GB25_ERR_CUDA;                                                   \
+      return GB25_ERR_CUDA;                                                                           \
+    }                                                                                                 \
+  } while (0)
+
+#define REQUIRE(h)                                                       \
+  do {                                                                   \
+    if (!(h)) return GB25_ERR_INVALID;                                   \
+    if ((h)->sticky) return (h)->sticky;                                 \
+    cudaError_t e0_ = cudaSetDevice((h)->device);                        \
+    if (e0_ != cudaSuccess) { (h)->err = cudaGetErrorString(e0_); (h)->sticky = GB25_ERR_CUDA; return GB25_ERR_CUDA; } \
+  } while (0)
+
+static int check_async(Handle* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    h->err = std::string(what) + ": " + cudaGetErrorString(e);
+    h->sticky = GB25_ERR_CUDA;
+    return GB25_ERR_CUDA;
+  }
+  return GB25_OK;
+}
+
+// ------------------------------------------------------------------ stage timers
+struct StageScope {
+  Handle* h; StageTimer* t = nullptr; size_t slot = 0;
+  StageScope(Handle* h_, const char* name) : h(h_) {
+    if (!h->timers_on) return;
+    for (auto& s : h->timers) if (s.name == name || !strcmp(s.name, name)) { t = &s; break; }
+    if (!t) { h->timers.push_back(StageTimer{name}); t = &h->timers.back(); }
+    if (t->used == t->ev.size()) {
+      cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+      t->ev.push_back({a, b});
+    }
+    slot = t->used++;
+    cudaEventRecord(t->ev[slot].first, h->stream);
+  }
+  ~StageScope() { if (t) cudaEventRecord(t->ev[slot].second, h->stream); }
+};
+static void drain_timers(Handle* h) {
+  for (auto& s : h->timers) {
+    for (size_t q = 0; q < s.used; q++) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, s.ev[q].first, s.ev[q].second) == cudaSuccess) { s.total_ms += ms; s.calls++; }
+    }
+    s.used = 0;
+  }
+}
+
+// ------------------------------------------------------------------ field table
+struct FieldInfo { int lx, ly, lz; bool three_d; };
+static const FieldInfo kFieldInfo[GB25_FIELD_COUNT] = {
+    {1, 0, 0, true},  {0, 1, 0, true},  {0, 0, 1, true},  {0, 0, 0, true},  {0, 0, 0, true},  {0, 0, 0, true},   // u v w T S p
+    {1, 0, 0, true},  {0, 1, 0, true},  {0, 0, 0, true},  {0, 0, 0, true},                                        // Gn
+    {1, 0, 0, true},  {0, 1, 0, true},  {0, 0, 0, true},  {0, 0, 0, true},                                        // G-
+    {0, 0, 1, false}, {1, 0, 0, false}, {0, 1, 0, false},                                                         // eta U V
+    {0, 0, 1, false}, {1, 0, 0, false}, {0, 1, 0, false},                                                         // filtered
+    {1, 0, 0, false}, {0, 1, 0, false}, {1, 0, 0, false}, {0, 1, 0, false}};                                      // Gn.U Gn.V G-.U G-.V
+
+static void parent_shape(const Handle* h, int field, int shape[3]) {
+  const FieldInfo& fi = kFieldInfo[field];
+  const gb25_config& c = h->cfg;
+  shape[0] = c.Nx + 2 * c.Hx;
+  shape[1] = c.Ny + 2 * c.Hy + ((fi.ly && c.topo_y == GB25_TOPO_BOUNDED) ? 1 : 0);
+  shape[2] = fi.three_d ? c.Nz + 2 * c.Hz + fi.lz : 1;
+}
+
+template <class T>
+static int upload(Handle* h, const T* host, size_t n, const T** out) {
+  T* d = nullptr;
+  CK(h, cudaMalloc(&d, n * sizeof(T)));
+  h->allocs.push_back(d);
+  CK(h, cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  *out = d;
+  return GB25_OK;
+}
+
+extern "C" int gb25_abi_version(void) { return GB25_ABI_VERSION; }
+
+extern "C" const char* gb25_last_error(const gb25_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+extern "C" int gb25_clear_error(gb25_handle* h) {
+  if (!h) return GB25_ERR_INVALID;
+  h->err.clear(); h->sticky = 0; cudaGetLastError();
+  return GB25_OK;
+}
+
+// ------------------------------------------------------------------ create / destroy
+static int build_immersed_products(Handle* h, const gb25_grid* grid) {
+  const gb25_config& c = h->cfg;
+  const int PX = c.Nx + 2 * c.Hx, PY = c.Ny + 2 * c.Hy + 1, PZ = c.Nz + 2 * c.Hz + 1;
+  const int n2 = PX * PY;
+  auto zf = [&](int k) { return grid->z_f[k + c.Hz - 1]; };
+  auto zc = [&](int k) { return grid->z_c[k + c.Hz - 1]; };
+  (void)PZ;
+  std::vector<short> kb(n2, 0), kbe(n2, 0);
+  std::vector<float> Hcc(n2), Hfc(n2), Hcf(n2);
+  const float ztop = zf(c.Nz + 1), zbot = zf(1);
+  for (int J = 0; J < PY; J++)
+    for (int I = 0; I < PX; I++) {
+      const int q = I + PX * J;
+      int k0 = 0;
+      if (c.immersed && grid->bottom_height) {
+        const float bh = std::min(std::max(grid->bottom_height[q], zbot), ztop);
+        for (int k = 1; k <= c.Nz; k++) if (zc(k) <= bh) k0 = k;
+      }
+      kb[q] = (short)k0;
+      Hcc[q] = ztop - zf(k0 + 1);
+      const int j = J - c.Hy + 1;
+      const bool yout = c.topo_y == GB25_TOPO_BOUNDED ? (j < 1 || j > c.Ny) : (c.south_inactive && j < 1);
+      kbe[q] = yout ? (short)GB25_BIG : (short)k0;
+    }
+  for (int J = 0; J < PY; J++)
+    for (int I = 0; I < PX; I++) {
+      const int q = I + PX * J, qw = std::max(I - 1, 0) + PX * J, qs = I + PX * std::max(J - 1, 0);
+      Hfc[q] = std::min(Hcc[qw], Hcc[q]);
+      Hcf[q] = std::min(Hcc[qs], Hcc[q]);
+    }
+  // order-reduction thresholds: buffer B allowed iff k > threshold (window maxima of the column rule)
+  auto at = [&](const std::vector<short>& a, int I, int J) -> int {
+    if (I < 0 || I >= PX || J < 0 || J >= PY) return GB25_BIG;  // beyond the stored halo: treat as solid
+    return a[I + PX * J];
+  };
+  std::vector<short> fx3(n2), fx2(n2), fy3(n2), fy2(n2), cx3(n2), cx2(n2), cy3(n2), cy2(n2), knear(n2);
+  for (int J = 0; J < PY; J++)
+    for (int I = 0; I < PX; I++) {
+      const int q = I + PX * J;
+      int m;
+      auto facemax = [&](int B, int dx, int dy) { int r = 0; for (int s = -B; s <= B - 1; s++) r = std::max(r, at(kbe, I + dx * s, J + dy * s)); return r; };
+      auto nodemax = [&](int B, int dx, int dy) {
+        int r = 0;
+        for (int s = -B + 1; s <= B; s++) r = std::max(r, std::min(at(kbe, I + dx * (s - 1), J + dy * (s - 1)), at(kbe, I + dx * s, J + dy * s)));
+        return r;
+      };
+      fx3[q] = (short)facemax(3, 1, 0); fx2[q] = (short)facemax(2, 1, 0);
+      fy3[q] = (short)facemax(3, 0, 1); fy2[q] = (short)facemax(2, 0, 1);
+      cx3[q] = (short)nodemax(3, 1, 0); cx2[q] = (short)nodemax(2, 1, 0);
+      cy3[q] = (short)nodemax(3, 0, 1); cy2[q] = (short)nodemax(2, 0, 1);
+      m = 0;
+      for (int dj = -4; dj <= 4; dj++) for (int di = -4; di <= 4; di++) m = std::max(m, at(kbe, I + di, J + dj));
+      knear[q] = (short)m;
+    }
+  int rc;
+  if ((rc = upload(h, kb.data(), n2, &h->g.kb))) return rc;
+  if ((rc = upload(h, fx3.data(), n2, &h->g.fx3))) return rc;
+  if ((rc = upload(h, fx2.data(), n2, &h->g.fx2))) return rc;
+  if ((rc = upload(h, fy3.data(), n2, &h->g.fy3))) return rc;
+  if ((rc = upload(h, fy2.data(), n2, &h->g.fy2))) return rc;
+  if ((rc = upload(h, cx3.data(), n2, &h->g.cx3))) return rc;
+  if ((rc = upload(h, cx2.data(), n2, &h->g.cx2))) return rc;
+  if ((rc = upload(h, cy3.data(), n2, &h->g.cy3))) return rc;
+  if ((rc = upload(h, cy2.data(), n2, &h->g.cy2))) return rc;
+  if ((rc = upload(h, knear.data(), n2, &h->g.knear))) return rc;
+  if ((rc = upload(h, Hfc.data(), n2, &h->g.Hfc))) return rc;
+  if ((rc = upload(h, Hcf.data(), n2, &h->g.Hcf))) return rc;
+  return GB25_OK;
+}
+
+extern "C" int gb25_destroy(gb25_handle* h) {
+  if (!h) return GB25_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->graph) cudaGraphDestroy(h->graph);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->stage_dev) cudaFree(h->stage_dev);
+  for (auto& s : h->timers) for (auto& e : s.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  if (h->loop_start) cudaEventDestroy(h->loop_start);
+  if (h->loop_stop) cudaEventDestroy(h->loop_stop);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return GB25_OK;
+}
+
+extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_handle** out) {
+  if (out) *out = nullptr;
+  if (!cfg || !grid || !out) { g_create_error = "gb25_create: null argument"; return GB25_ERR_INVALID; }
+  if (cfg->Nx < 8 || cfg->Ny < 8 || cfg->Nz < 1 || cfg->Hx < 4 || cfg->Hy < 4 || cfg->Hz < 4 || cfg->nsubsteps < 1 ||
+      cfg->nsubsteps > 256 || cfg->Nz > 32000) {
+    g_create_error = "gb25_create: unsupported sizes (need Nx,Ny >= 8, halo >= 4, 1 <= nsubsteps <= 256)";
+    return GB25_ERR_INVALID;
+  }
+  if (cfg->topo_y == GB25_TOPO_FOLD && (cfg->Nx % 2)) { g_create_error = "gb25_create: tripolar fold needs even Nx"; return GB25_ERR_INVALID; }
+  if (!grid->dx_cc || !grid->z_f || !grid->z_c || !grid->dz_c || !grid->dz_f || !grid->avg_weights || !grid->f_ff) {
+    g_create_error = "gb25_create: missing grid array"; return GB25_ERR_INVALID;
+  }
+  if (cfg->Rx < 1 || cfg->Ry < 1 || cfg->rx < 0 || cfg->rx >= cfg->Rx || cfg->ry < 0 || cfg->ry >= cfg->Ry) {
+    g_create_error = "gb25_create: bad partition (Rx, Ry, rx, ry)"; return GB25_ERR_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("gb25_create: no CUDA device available (libgb25cuda has no CPU path): ") +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    cudaGetLastError();
+    return GB25_ERR_NO_DEVICE;
+  }
+  Handle* h = new Handle();
+  h->timers.reserve(64);
+  h->cfg = *cfg;
+  if (cfg->device >= 0) h->device = cfg->device; else cudaGetDevice(&h->device);
+  if ((e = cudaSetDevice(h->device)) != cudaSuccess) {
+    g_create_error = std::string("gb25_create: cudaSetDevice: ") + cudaGetErrorString(e);
+    delete h; return GB25_ERR_NO_DEVICE;
+  }
+#define CKC(call)                                                                         \
+  do { int rc_ = (call); if (rc_ != GB25_OK) { g_create_error = h->err; gb25_destroy(h); return rc_; } } while (0)
+  auto ckcuda = [&](cudaError_t ce, const char* what) -> int {
+    if (ce != cudaSuccess) { h->err = std::string(what) + ": " + cudaGetErrorString(ce); return GB25_ERR_CUDA; }
+    return GB25_OK;
+  };
+  CKC(ckcuda(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
+  CKC(ckcuda(cudaEventCreate(&h->loop_start), "cudaEventCreate"));
+  CKC(ckcuda(cudaEventCreate(&h->loop_stop), "cudaEventCreate"));
+  DevGrid& g = h->g;
+  g.Nx = cfg->Nx; g.Ny = cfg->Ny; g.Nz = cfg->Nz; g.Hx = cfg->Hx; g.Hy = cfg->Hy; g.Hz = cfg->Hz;
+  g.PX = g.Nx + 2 * g.Hx; g.PY = g.Ny + 2 * g.Hy + 1; g.PZ = g.Nz + 2 * g.Hz + 1;
+  if ((double)g.PX * g.PY * g.PZ > 2.0e9) { g_create_error = "gb25_create: tile too large for 32-bit plane offsets"; gb25_destroy(h); return GB25_ERR_INVALID; }
+  g.n2 = g.PX * g.PY;
+  g.topo_y = cfg->topo_y; g.immersed = cfg->immersed && grid->bottom_height; g.coriolis_scheme = cfg->coriolis_scheme;
+  g.fold_variant = cfg->fold_variant; g.south_inactive = cfg->south_inactive; g.cond_diff = cfg->cond_diff; g.eos_r0 = cfg->eos_r0;
+  g.g = cfg->g; g.rho0 = cfg->rho0; g.eps = cfg->weno_eps;
+  h->cfg.immersed = g.immersed;
+  const size_t n2 = g.n2, n3 = n2 * g.PZ;
+  const float* src2[13] = {grid->dx_cc, grid->dx_fc, grid->dx_cf, grid->dx_ff, grid->dy_cc, grid->dy_fc, grid->dy_cf, grid->dy_ff,
+                           grid->az_cc, grid->az_fc, grid->az_cf, grid->az_ff, grid->f_ff};
+  const float** dst2[13] = {&g.dxcc, &g.dxfc, &g.dxcf, &g.dxff, &g.dycc, &g.dyfc, &g.dycf, &g.dyff, &g.azcc, &g.azfc, &g.azcf, &g.azff, &g.fff};
+  for (int a = 0; a < 13; a++) {
+    if (!src2[a]) { g_create_error = "gb25_create: missing metric array"; gb25_destroy(h); return GB25_ERR_INVALID; }
+    CKC(upload(h, src2[a], n2, dst2[a]));
+  }
+  const float* srcz[4] = {grid->z_f, grid->z_c, grid->dz_c, grid->dz_f};
+  const float** dstz[4] = {&g.zf, &g.zc, &g.dzc, &g.dzf};
+  for (int a = 0; a < 4; a++) CKC(upload(h, srcz[a], (size_t)g.PZ, dstz[a]));
+  CKC(build_immersed_products(h, grid));
+  h->weights.assign(grid->avg_weights, grid->avg_weights + cfg->nsubsteps);
+  // fields
+  for (int fidx = 0; fidx < GB25_FIELD_COUNT; fidx++) {
+    const size_t n = kFieldInfo[fidx].three_d ? n3 : n2;
+    float* d = nullptr;
+    cudaError_t ce = cudaMalloc(&d, n * sizeof(float));
+    if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc field: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
+    h->allocs.push_back(d);
+    CKC(ckcuda(cudaMemsetAsync(d, 0, n * sizeof(float), h->stream), "cudaMemset"));
+    h->field_ptr[fidx] = d;
+  }
+  DevFields& f = h->f;
+  f.u = h->field_ptr[GB25_U]; f.v = h->field_ptr[GB25_V]; f.w = h->field_ptr[GB25_W];
+  f.T = h->field_ptr[GB25_T]; f.S = h->field_ptr[GB25_S]; f.p = h->field_ptr[GB25_P];
+  for (int q = 0; q < 4; q++) { f.gn[q] = h->field_ptr[GB25_GN_U + q]; f.gm[q] = h->field_ptr[GB25_GM_U + q]; }
+  f.eta = h->field_ptr[GB25_ETA]; f.bu = h->field_ptr[GB25_BARO_U]; f.bv = h->field_ptr[GB25_BARO_V];
+  f.feta = h->field_ptr[GB25_FILT_ETA]; f.fu = h->field_ptr[GB25_FILT_U]; f.fv = h->field_ptr[GB25_FILT_V];
+  f.gU = h->field_ptr[GB25_GN_BARO_U]; f.gV = h->field_ptr[GB25_GN_BARO_V];
+  f.gmU = h->field_ptr[GB25_GM_BARO_U]; f.gmV = h->field_ptr[GB25_GM_BARO_V];
+  h->stage_elems = n3;
+  {
+    cudaError_t ce = cudaMalloc(&h->stage_dev, n3 * sizeof(float));
+    if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc staging: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
+  }
+  CKC(ckcuda(cudaStreamSynchronize(h->stream), "create sync"));
+#undef CKC
+  *out = h;
+  return GB25_OK;
+}
+
+// ------------------------------------------------------------------ transfers (parent shape <-> internal layout)
+extern "C" int gb25_field_shape(const gb25_handle* h, int field, int shape[3]) {
+  if (!h || field < 0 || field >= GB25_FIELD_COUNT || !shape) return GB25_ERR_INVALID;
+  parent_shape(h, field, shape);
+  return GB25_OK;
+}
+static int copy_field(Handle* h, int field, float* host, bool to_device) {
+  if (field < 0 || field >= GB25_FIELD_COUNT || !host) { h->err = "bad field id or null buffer"; return GB25_ERR_INVALID; }
+  int s[3];
+  parent_shape(h, field, s);
+  const DevGrid& g = h->g;
+  cudaMemcpy3DParms p = {};
+  p.extent = make_cudaExtent((size_t)s[0] * sizeof(float), s[1], s[2]);
+  cudaPitchedPtr hp = make_cudaPitchedPtr(host, (size_t)s[0] * sizeof(float), s[0], s[1]);
+  cudaPitchedPtr dp = make_cudaPitchedPtr(h->field_ptr[field], (size_t)g.PX * sizeof(float), g.PX, g.PY);
+  if (to_device) { p.srcPtr = hp; p.dstPtr = dp; p.kind = cudaMemcpyHostToDevice; }
+  else { p.srcPtr = dp; p.dstPtr = hp; p.kind = cudaMemcpyDeviceToHost; }
+  CK(h, cudaMemcpy3DAsync(&p, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  return GB25_OK;
+}
+extern "C" int gb25_set_field(gb25_handle* h, int field, const float* host_parent) {
+  REQUIRE(h);
+  return copy_field(h, field, const_cast<float*>(host_parent), true);
+}
+extern "C" int gb25_get_field(gb25_handle* h, int field, float* host_parent) {
+  REQUIRE(h);
+  return copy_field(h, field, host_parent, false);
+}
+extern "C" int gb25_set_clock(gb25_handle* h, double time, long iteration, float last_dt) {
+  if (!h) return GB25_ERR_INVALID;
+  h->time = time; h->iteration = iteration; h->last_dt = last_dt;
+  return GB25_OK;
+}
+extern "C" int gb25_get_clock(const gb25_handle* h, double* time, long* iteration, float* last_dt) {
+  if (!h) return GB25_ERR_INVALID;
+  if (time) *time = h->time;
+  if (iteration) *iteration = h->iteration;
+  if (last_dt) *last_dt = h->last_dt;
+  return GB25_OK;
+}
+extern "C" int gb25_synchronize(gb25_handle* h) {
+  REQUIRE(h);
+  CK(h, cudaStreamSynchronize(h->stream));
+  return check_async(h, "gb25_synchronize");
+}
+
+// ------------------------------------------------------------------ stages
+static void fill_prognostic(Handle* h) {
+  StageScope t(h, "fill_halo_regions");
+  DevFields& f = h->f;
+  HaloSpec s3[4] = {{f.u, 1, 0, 0, -1.f}, {f.v, 0, 1, 0, -1.f}, {f.T, 0, 0, 0, 1.f}, {f.S, 0, 0, 0, 1.f}};
+  launch_fill_halo(h, s3, 4, true);
+  HaloSpec s2[3] = {{f.eta, 0, 0, 1, 1.f}, {f.bu, 1, 0, 0, -1.f}, {f.bv, 0, 1, 0, -1.f}};
+  launch_fill_halo(h, s2, 3, false);
+}
+static void stage_mask(Handle* h) { StageScope t(h, "mask_immersed_fields"); launch_mask(h, false); }
+static void stage_aux(Handle* h) {
+  { StageScope t(h, "compute_w_from_continuity"); launch_compute_w(h); }
+  { StageScope t(h, "update_hydrostatic_pressure"); launch_compute_p(h); }
+}
+static void stage_tend(Handle* h) {
+  { StageScope t(h, "momentum_tendencies"); launch_momentum_tendency(h); }
+  { StageScope t(h, "tracer_tendencies"); launch_tracer_tendency(h); }
+}
+static void stage_update_state(Handle* h) {
+  stage_mask(h);
+  fill_prognostic(h);
+  stage_aux(h);
+  stage_tend(h);
+}
+static void stage_ab2(Handle* h, float dt, float chi) {
+  DevFields& f = h->f;
+  { StageScope t(h, "ab2_step_fields"); launch_ab2_columns(h, dt, chi); }
+  {
+    StageScope t(h, "split_explicit_free_surface");
+    HaloSpec sg[2] = {{f.gU, 1, 0, 0, -1.f}, {f.gV, 0, 1, 0, -1.f}};
+    launch_fill_halo(h, sg, 2, false);
+    launch_barotropic(h, dt);
+    launch_mask(h, true);
+    HaloSpec sb[2] = {{f.bu, 1, 0, 0, -1.f}, {f.bv, 0, 1, 0, -1.f}};
+    launch_fill_halo(h, sb, 2, false);
+  }
+}
+static void stage_correct(Handle* h) { StageScope t(h, "correct_velocities_and_cache"); launch_correct_cache(h); }
+static void stage_initialize(Handle* h) {
+  StageScope t(h, "initialize");
+  launch_barotropic_mode(h);
+  HaloSpec sb[2] = {{h->f.bu, 1, 0, 0, -1.f}, {h->f.bv, 0, 1, 0, -1.f}};
+  launch_fill_halo(h, sb, 2, false);
+}
+static void one_time_step(Handle* h, float dt, bool euler) {
+  euler = euler || (dt != h->last_dt);
+  const float chi = euler ? -0.5f : h->cfg.chi;
+  stage_ab2(h, dt, chi);
+  h->time += (double)dt; h->iteration += 1; h->last_dt = dt;
+  stage_correct(h);
+  stage_update_state(h);
+}
+
+extern "C" int gb25_initialize(gb25_handle* h) { REQUIRE(h); stage_initialize(h); return check_async(h, "gb25_initialize"); }
+extern "C" int gb25_update_state(gb25_handle* h) { REQUIRE(h); stage_update_state(h); return check_async(h, "gb25_update_state"); }
+extern "C" int gb25_first_time_step(gb25_handle* h, float dt) {
+  REQUIRE(h);
+  if (dt <= 0.f) dt = h->last_dt;
+  stage_initialize(h);
+  stage_update_state(h);
+  one_time_step(h, dt, true);
+  return check_async(h, "gb25_first_time_step");
+}
+extern "C" int gb25_time_step(gb25_handle* h, float dt) {
+  REQUIRE(h);
+  if (dt <= 0.f) dt = h->last_dt;
+  one_time_step(h, dt, false);
+  return check_async(h, "gb25_time_step");
+}
+extern "C" int gb25_loop(gb25_handle* h, float dt, int nsteps) {
+  REQUIRE(h);
+  if (nsteps < 0) { h->err = "gb25_loop: negative step count"; return GB25_ERR_INVALID; }
+  if (dt <= 0.f) dt = h->last_dt;
+  CK(h, cudaEventRecord(h->loop_start, h->stream));
+  for (int n = 0; n < nsteps; n++) one_time_step(h, dt, false);
+  CK(h, cudaEventRecord(h->loop_stop, h->stream));
+  h->loop_timed = true;
+  return check_async(h, "gb25_loop");
+}
+extern "C" int gb25_mask_immersed_fields(gb25_handle* h) { REQUIRE(h); stage_mask(h); return check_async(h, "gb25_mask_immersed_fields"); }
+extern "C" int gb25_fill_halo_regions(gb25_handle* h) { REQUIRE(h); fill_prognostic(h); return check_async(h, "gb25_fill_halo_regions"); }
+extern "C" int gb25_compute_auxiliaries(gb25_handle* h) { REQUIRE(h); stage_aux(h); return check_async(h, "gb25_compute_auxiliaries"); }
+extern "C" int gb25_compute_tendencies(gb25_handle* h) { REQUIRE(h); stage_tend(h); return check_async(h, "gb25_compute_tendencies"); }
+extern "C" int gb25_compute_momentum_tendencies(gb25_handle* h) {
+  REQUIRE(h);
+  { StageScope t(h, "momentum_tendencies"); launch_momentum_tendency(h); }
+  return check_async(h, "gb25_compute_momentum_tendencies");
+}
+extern "C" int gb25_compute_tracer_tendencies(gb25_handle* h) {
+  REQUIRE(h);
+  { StageScope t(h, "tracer_tendencies"); launch_tracer_tendency(h); }
+  return check_async(h, "gb25_compute_tracer_tendencies");
+}
+extern "C" int gb25_ab2_step(gb25_handle* h, float dt, float chi) {
+  REQUIRE(h);
+  if (dt <= 0.f) dt = h->last_dt;
+  stage_ab2(h, dt, chi);
+  return check_async(h, "gb25_ab2_step");
+}
+extern "C" int gb25_correct_velocities_and_cache_previous_tendencies(gb25_handle* h) {
+  REQUIRE(h);
+  stage_correct(h);
+  return check_async(h, "gb25_correct_velocities_and_cache_previous_tendencies");
+}
+
+// ------------------------------------------------------------------ measurement
+extern "C" int gb25_last_loop_seconds(gb25_handle* h, double* seconds) {
+  REQUIRE(h);
+  if (!seconds || !h->loop_timed) { h->err = "gb25_last_loop_seconds: no loop has been timed"; return GB25_ERR_INVALID; }
+  CK(h, cudaEventSynchronize(h->loop_stop));
+  float ms = 0.f;
+  CK(h, cudaEventElapsedTime(&ms, h->loop_start, h->loop_stop));
+  *seconds = (double)ms * 1e-3;
+  return GB25_OK;
+}
+extern "C" int gb25_kernel_launch_count(const gb25_handle* h, long* launches) {
+  if (!h || !launches) return GB25_ERR_INVALID;
+  *launches = h->launches;
+  return GB25_OK;
+}
+extern "C" int gb25_enable_stage_timers(gb25_handle* h, int enable) {
+  REQUIRE(h);
+  CK(h, cudaStreamSynchronize(h->stream));
+  drain_timers(h);
+  h->timers_on = enable != 0;
+  if (enable) for (auto& s : h->timers) { s.total_ms = 0.f; s.calls = 0; }
+  return GB25_OK;
+}
+extern "C" int gb25_get_stage_times(gb25_handle* h, const char** names, float* ms, long* calls, int cap) {
+  REQUIRE(h);
+  CK(h, cudaStreamSynchronize(h->stream));
+  drain_timers(h);
+  int n = 0;
+  for (auto& s : h->timers) {
+    if (n >= cap) break;
+    if (names) names[n] = s.name;
+    if (ms) ms[n] = s.total_ms;
+    if (calls) calls[n] = s.calls;
+    n++;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------ multi-GPU exchange (see gb25_exchange.cu)
+extern "C" int gb25_exchange_blob_size(void) { return 0; }
+extern "C" int gb25_exchange_export(gb25_handle* h, void*) {
+  if (!h) return GB25_ERR_INVALID;
+  h->err = "gb25_exchange_export: multi-GPU exchange is not built yet"; return GB25_ERR_COMM;
+}
+extern "C" int gb25_exchange_connect(gb25_handle* h, const void*, int) {
+  if (!h) return GB25_ERR_INVALID;
+  h->err = "gb25_exchange_connect: multi-GPU exchange is not built yet"; return GB25_ERR_COMM;
+}

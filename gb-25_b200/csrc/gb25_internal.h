@@ -1,0 +1,67 @@
+// gb25_internal.h — host-side handle and launcher declarations shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gb25cuda.h"
+#include "gb25_device.cuh"
+
+struct HaloSpec { float* a; int lx, ly, lz; float sign; };
+
+struct StageTimer {
+  const char* name;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  size_t used = 0;
+  float total_ms = 0.f;
+  long calls = 0;
+};
+
+struct gb25_handle {
+  gb25_config cfg;
+  DevGrid g;
+  DevFields f;
+  cudaStream_t stream = nullptr;
+  int device = 0;
+  std::vector<float> weights;
+  std::vector<void*> allocs;
+  float* field_ptr[GB25_FIELD_COUNT];
+  // clock (model.clock)
+  double time = 0.0;
+  long iteration = 0;
+  float last_dt = 0.f;
+  // errors
+  std::string err;
+  int sticky = 0;
+  // measurement
+  long launches = 0;
+  cudaEvent_t loop_start = nullptr, loop_stop = nullptr;
+  bool loop_timed = false;
+  bool timers_on = false;
+  std::vector<StageTimer> timers;
+  // staging for parent-shaped transfers
+  float* stage_dev = nullptr;
+  size_t stage_elems = 0;
+  // CUDA graph of one AB2 step (captured lazily for gb25_loop)
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  float graph_dt = 0.f;
+  long graph_launches = 0;
+  bool use_fused = true;
+
+  inline void count_launch() { launches++; }
+};
+typedef gb25_handle Handle;
+
+// stage launchers (gb25_kernels.cu)
+void launch_fill_halo(Handle* h, const HaloSpec* specs, int n, bool three_d);
+void launch_mask(Handle* h, bool uv_only);
+void launch_compute_w(Handle* h);
+void launch_compute_p(Handle* h);
+void launch_tracer_tendency(Handle* h);
+void launch_momentum_tendency(Handle* h);
+void launch_ab2_columns(Handle* h, float dt, float chi);
+void launch_barotropic(Handle* h, float dt);
+void launch_correct_cache(Handle* h);
+void launch_barotropic_mode(Handle* h);

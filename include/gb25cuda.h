@@ -1,0 +1,155 @@
+/* gb25cuda.h — C ABI of libgb25cuda: the B200-native (sm_100a) implementation of the Oceananigans
+ * HydrostaticFreeSurfaceModel time step that PRONTOLab/GB-25 drives.
+ *
+ * Every entry point cites the reference interface it replaces (paths under /root/reference).
+ * The reference host stays Julia: the GordonBell25 constructors and first_time_step!/time_step!/
+ * loop! are kept, and call these symbols through `ccall` (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *  - plain C types only; host arrays are borrowed for the duration of the call;
+ *  - all arrays are Float32, column-major with x fastest and halos included ("parent" arrays of
+ *    Oceananigans fields): a (Tx,Ty,Tz) Julia array is passed as-is;
+ *  - every function returns 0 on success and a negative gb25_status otherwise; the message of the
+ *    last failure is available from gb25_last_error(); no exception crosses the boundary;
+ *  - a handle is driven by one thread at a time; compute calls are stream-ordered and asynchronous,
+ *    gb25_get_field / gb25_synchronize / timing queries block;
+ *  - there is no CPU fallback: with no usable CUDA device gb25_create fails with GB25_ERR_NO_DEVICE.
+ */
+#ifndef GB25CUDA_H
+#define GB25CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB25_ABI_VERSION 1
+
+typedef struct gb25_handle gb25_handle;
+
+typedef enum {
+  GB25_OK = 0,
+  GB25_ERR_INVALID = -1,    /* bad argument / unsupported configuration */
+  GB25_ERR_NO_DEVICE = -2,  /* no CUDA device: the product has no CPU path */
+  GB25_ERR_CUDA = -3,       /* CUDA runtime error (sticky until gb25_clear_error) */
+  GB25_ERR_ALLOC = -4,
+  GB25_ERR_COMM = -5        /* multi-GPU exchange set-up / transport error */
+} gb25_status;
+
+/* y topology of the horizontal grid */
+#define GB25_TOPO_BOUNDED 0 /* LatitudeLongitudeGrid: (Periodic, Bounded, Bounded)            */
+#define GB25_TOPO_FOLD 1    /* TripolarGrid: (Periodic, RightConnected, Bounded), zipper fold */
+
+/* Model configuration: what HydrostaticFreeSurfaceModel(; grid, free_surface, buoyancy, coriolis,
+ * momentum_advection, tracer_advection) fixes in src/baroclinic_instability_model.jl:17-70.
+ * Sizes are those of THIS handle's tile (the whole domain when Rx = Ry = 1). */
+typedef struct {
+  int Nx, Ny, Nz;          /* interior size of this tile                                           */
+  int Hx, Hy, Hz;          /* halo (8,8,8) in the reference: src/baroclinic_instability_model.jl:18 */
+  int topo_y;              /* GB25_TOPO_*                                                          */
+  int immersed;            /* 1: ImmersedBoundaryGrid(GridFittedBottom) (src/model_utils.jl:143)   */
+  int nsubsteps;           /* barotropic substeps actually taken = length(averaging_weights)       */
+  int coriolis_scheme;     /* 0 EnstrophyConserving, 1 ActiveCellEnstrophyConserving   (decision U2)  */
+  int fold_variant;        /* 0 plain zipper, 1 also overwrite redundant half of row Ny (decision U1) */
+  int south_inactive;      /* tripolar: cells south of j=1 are outside the domain      (decision U4)  */
+  int cond_diff;           /* immersed-aware differences in vorticity and grad p       (decision U15) */
+  int eos_r0;              /* include r0(z) in TEOS-10 rho'                            (decision U8)  */
+  float g;                 /* 9.80665                                                              */
+  float rho0;              /* 1020 (TEOS-10 reference density)                                     */
+  float chi;               /* 0.1 (QuasiAdamsBashforth2)                                           */
+  float dtau_frac;         /* barotropic step as a fraction of dt = 2/substeps                     */
+  float weno_eps;          /* 1e-8                                                                 */
+  /* x/y partition: Distributed(arch; partition=Partition(Rx,Ry,1)),
+   * sharding/sharded_baroclinic_instability_simulation_run.jl:65-72; rank = rx + Rx*ry */
+  int Rx, Ry, rx, ry;
+  int device;              /* CUDA device ordinal to use (-1: current device)                      */
+} gb25_config;
+
+/* Grid products, all host pointers.  2-D arrays have (Nx+2Hx) x (Ny+2Hy+1) elements, x fastest;
+ * interior (i,j) (1-based) at [(i+Hx-1) + (Nx+2Hx)*(j+Hy-1)]; the last row is only read for
+ * Face-in-y quantities on Bounded grids.  Vertical arrays have Nz+2Hz+1 elements, k at [k+Hz-1].
+ * Replaces what the kernels read from `grid` (grid.Δxᶠᶜᵃ, grid.Azᶜᶜᵃ, grid.z.cᵃᵃᶠ, …,
+ * ibg.immersed_boundary.bottom_height) — built on the host by src/model_utils.jl:56-65,134-146. */
+typedef struct {
+  const float *dx_cc, *dx_fc, *dx_cf, *dx_ff;
+  const float *dy_cc, *dy_fc, *dy_cf, *dy_ff;
+  const float *az_cc, *az_fc, *az_cf, *az_ff;
+  const float *f_ff;            /* 2 Ω sin φ at (Face,Face): HydrostaticSphericalCoriolis           */
+  const float *z_f, *z_c;       /* face / centre heights                                            */
+  const float *dz_c, *dz_f;     /* Δz at centres (zf[k+1]-zf[k]) and at faces (zc[k]-zc[k-1])       */
+  const float *bottom_height;   /* GridFittedBottom height at (C,C), or NULL when not immersed       */
+  const float *avg_weights;     /* nsubsteps split-explicit averaging weights                        */
+} gb25_grid;
+
+/* Field identifiers for gb25_set_field / gb25_get_field / gb25_field_shape.
+ * = Oceananigans.fields(model), timestepper.Gⁿ / G⁻, free_surface.{η, barotropic_velocities,
+ *   filtered_state}: exactly the arrays src/correctness.jl:28-90 compares. */
+typedef enum {
+  GB25_U = 0, GB25_V, GB25_W, GB25_T, GB25_S, GB25_P,
+  GB25_GN_U, GB25_GN_V, GB25_GN_T, GB25_GN_S,
+  GB25_GM_U, GB25_GM_V, GB25_GM_T, GB25_GM_S,
+  GB25_ETA, GB25_BARO_U, GB25_BARO_V,
+  GB25_FILT_ETA, GB25_FILT_U, GB25_FILT_V,
+  GB25_GN_BARO_U, GB25_GN_BARO_V, GB25_GM_BARO_U, GB25_GM_BARO_V,
+  GB25_FIELD_COUNT
+} gb25_field;
+
+int gb25_abi_version(void);
+
+/* Construction / destruction.  Replaces the device-side allocation done by
+ * HydrostaticFreeSurfaceModel(...) (src/baroclinic_instability_model.jl:67-70). */
+int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_handle** out);
+int gb25_destroy(gb25_handle* h);
+const char* gb25_last_error(const gb25_handle* h); /* h may be NULL: error of a failed gb25_create */
+int gb25_clear_error(gb25_handle* h);
+
+/* State transfer in Oceananigans parent shape.  Replaces sync_states! (src/correctness.jl:92-103)
+ * and the Array(parent(ψ)) reads of compare_parent (src/correctness.jl:4-15). */
+int gb25_field_shape(const gb25_handle* h, int field, int shape[3]);
+int gb25_set_field(gb25_handle* h, int field, const float* host_parent);
+int gb25_get_field(gb25_handle* h, int field, float* host_parent);
+/* model.clock: time, iteration, last_Δt (src/baroclinic_instability_model.jl:82) */
+int gb25_set_clock(gb25_handle* h, double time, long iteration, float last_dt);
+int gb25_get_clock(const gb25_handle* h, double* time, long* iteration, float* last_dt);
+
+/* Whole-step API.  Replaces Oceananigans.initialize!, TimeSteppers.update_state!
+ * (correctness/correctness_baroclinic_instability_simulation_run.jl:50-54) and
+ * GordonBell25.first_time_step! / time_step! / loop! (src/timestepping_utils.jl:21-45).
+ * dt <= 0 means "use clock.last_Δt" exactly as the reference wrappers do. */
+int gb25_initialize(gb25_handle* h);
+int gb25_update_state(gb25_handle* h);
+int gb25_first_time_step(gb25_handle* h, float dt);
+int gb25_time_step(gb25_handle* h, float dt);
+int gb25_loop(gb25_handle* h, float dt, int nsteps); /* no host synchronisation inside */
+int gb25_synchronize(gb25_handle* h);
+
+/* Operator-level API: one entry point per *_workload! of src/precompile.jl:44-127. */
+int gb25_mask_immersed_fields(gb25_handle* h);       /* precompile.jl:34  mask_immersed_model_fields!      */
+int gb25_fill_halo_regions(gb25_handle* h);          /* precompile.jl:44-46 tupled_fill_halo_regions!      */
+int gb25_compute_auxiliaries(gb25_handle* h);        /* precompile.jl:113-115 (w from continuity, pHY')    */
+int gb25_compute_tendencies(gb25_handle* h);         /* precompile.jl:48-50                                */
+int gb25_compute_momentum_tendencies(gb25_handle* h);/* precompile.jl:63-73                                */
+int gb25_compute_tracer_tendencies(gb25_handle* h);  /* precompile.jl:75-111                               */
+int gb25_ab2_step(gb25_handle* h, float dt, float chi); /* precompile.jl:121-123 (incl. split-explicit)    */
+int gb25_correct_velocities_and_cache_previous_tendencies(gb25_handle* h); /* precompile.jl:125-127         */
+
+/* Measurement: CUDA-event time of the last gb25_loop / per-stage accumulated times. */
+int gb25_last_loop_seconds(gb25_handle* h, double* seconds);
+int gb25_kernel_launch_count(const gb25_handle* h, long* launches);
+/* stage timers (CUDA events on the handle's stream): enable, then read after gb25_synchronize.
+ * names/ms must hold `cap` entries; returns the number of stages written. */
+int gb25_enable_stage_timers(gb25_handle* h, int enable);
+int gb25_get_stage_times(gb25_handle* h, const char** names, float* ms, long* calls, int cap);
+
+/* Multi-GPU (one process per GPU).  Neighbour tiles exchange halos over NVLink through peer-mapped
+ * memory: every rank exports its exchange window (gb25_exchange_export), the host side gathers the
+ * opaque blobs from all ranks (any transport: torch.distributed, MPI, a file) and hands the full set
+ * back (gb25_exchange_connect).  Replaces the XLA collective-permute halo traffic of
+ * Distributed(ReactantState(); partition=Partition(Rx,Ry,1)). */
+int gb25_exchange_blob_size(void);
+int gb25_exchange_export(gb25_handle* h, void* blob);
+int gb25_exchange_connect(gb25_handle* h, const void* blobs, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GB25CUDA_H */

@@ -1,0 +1,99 @@
+"""CPU-side checks of the boundary and the host logic: the C-ABI library loads and exports every symbol
+include/gb25cuda.h declares, fails loudly without a device, and the host mirror follows the reference."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gb25_b200 import grids, lib as L, model as M, sharding
+from gb25_b200.config import PhysicsConfig
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol(cuda_lib):
+    hdr = open(os.path.join(ROOT, "include", "gb25cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(gb25_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(cuda_lib, name), f"{name} declared in gb25cuda.h but not exported"
+    assert sorted(L.EXPORTED_SYMBOLS) == declared
+    assert cuda_lib.gb25_abi_version() == 1
+
+
+def test_signatures_carry_no_torch_or_cxx_types():
+    hdr = open(os.path.join(ROOT, "include", "gb25cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    assert "torch" not in hdr and "std::" not in hdr and "at::" not in hdr
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device error path")
+def test_create_fails_loudly_without_a_device(cuda_lib):
+    g = grids.simple_latitude_longitude_grid(16, 16, 4)
+    with pytest.raises(L.Gb25Error) as ei:
+        M.HydrostaticFreeSurfaceModel(M.B200(0), g)
+    assert ei.value.code == L.GB25_ERR_NO_DEVICE
+    assert "no CPU path" in str(ei.value)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the package or csrc may reference it."""
+    pkg = os.path.join(ROOT, "gb-25_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dp, fn), errors="ignore").read()
+                assert "gb25_oracle" not in src and "libgb25oracle" not in src, fn
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_arch_must_be_b200():
+    g = grids.simple_latitude_longitude_grid(16, 16, 4)
+    with pytest.raises(TypeError):
+        M.HydrostaticFreeSurfaceModel("CPU", g)
+    with pytest.raises(ValueError):
+        M.make_grid(16, 16, 4, grid_type="cubed_sphere")
+    with pytest.raises(TypeError):
+        M.baroclinic_instability_model(M.B200(), 16, 16, 4)      # Δt is a required keyword, as in the reference
+
+
+def test_factors_matches_reference_rule():
+    # /root/reference/src/sharding_utils.jl:39-62
+    assert sharding.factors(2) == (2, 1) and sharding.factors(8) == (4, 2) and sharding.factors(32) == (8, 4)
+    assert sharding.factors(4) == (2, 2) and sharding.factors(16) == (4, 4) and sharding.factors(9180) == (135, 68)
+    with pytest.raises(ValueError):
+        sharding.factors(3)
+    with pytest.raises(ValueError):
+        sharding.factors(6)
+    assert sharding.global_size_from_tile(1536, 768, 4, 2) == (1536 * 4 - 16, 768 * 2 - 16)
+    assert grids.resolution_to_points(8) == (48, 24)      # simulations/baroclinic_instability_simulation_run.jl:12-18
+
+
+def test_field_shapes_follow_oceananigans_parents():
+    g = grids.simple_latitude_longitude_grid(32, 16, 8)
+    assert g.field_shape((0, 0, 0)) == (48, 32, 24)
+    assert g.field_shape((0, 1, 0)) == (48, 33, 24)        # Bounded Face has N+1 points
+    assert g.field_shape((0, 0, 1)) == (48, 32, 25)
+    t = grids.tripolar_grid(32, 16, 8)
+    assert t.field_shape((0, 1, 0)) == (48, 32, 24)        # RightConnected Face has N points
+
+
+def test_isapprox_is_norm_based_like_julia():
+    a = np.ones((2, 3, 4), dtype=np.float32)
+    b = a.copy(); b[0, 0, 0] += 1e-3
+    assert M.compare_parent("x", a, b, rtol=1e-3, atol=0, verbose=False)          # 1e-3/sqrt(24) < 1e-3
+    assert not M.compare_parent("x", a, b, rtol=1e-5, atol=0, verbose=False)
+    assert not M.compare_parent("x", a, b, rtol=1e-3, atol=0, verbose=False, elementwise=1e-4)
+    c = a.copy(); c[0, 0, 0] = np.nan
+    assert not M.compare_parent("x", a, c, rtol=1.0, atol=0, verbose=False)

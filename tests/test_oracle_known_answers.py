@@ -1,0 +1,220 @@
+"""Pins the CPU oracle with self-contained known answers (no Julia, no reference vectors exist:
+/root/reference ships none — SURVEY.md §8c).  Everything here runs on CPU."""
+import numpy as np
+import pytest
+
+from gb25_b200 import grids, model as M
+from gb25_b200.splitexplicit import averaging_weights
+
+
+@pytest.fixture(scope="module")
+def small64(oracle_mod):
+    g = grids.simple_latitude_longitude_grid(32, 16, 6)
+    return oracle_mod.OracleModel(oracle_mod.CPUOracle(np.float64), g)
+
+
+def test_teos10_check_value(small64):
+    # Roquet et al. (2015) polyTEOS10-55t check value: r'(SA=35.5 g/kg, CT=3 degC, 3000 m) = 1028.21993233072
+    rho = small64.rho_prime(3.0, 35.5, -3000.0) + 1020.0
+    assert abs(rho - 1028.21993233072) < 2e-7    # coefficients are rounded to Float32-precision inputs (rho0)
+    # surface, fresh and warm water is lighter than cold salty water
+    assert small64.rho_prime(25.0, 30.0, 0.0) < small64.rho_prime(2.0, 36.0, 0.0)
+
+
+def test_weno5_exact_on_quadratics(small64):
+    # cell averages of x^2 over [m, m+1]; the face between window cells 2 and 3 sits at x = 3
+    m = np.arange(6, dtype=np.float64)
+    q = m * m + m + 1.0 / 3.0
+    for left in (True, False):
+        assert abs(small64.weno(3, left, q) - 9.0) < 1e-12
+        assert abs(small64.weno(2, left, q[1:5]) - 9.0) < 0.5      # WENO3 is exact for linear data only
+    lin = 2.0 * (m + 0.5) - 1.0
+    for left in (True, False):
+        assert abs(small64.weno(2, left, lin[1:5]) - 5.0) < 1e-12
+        assert abs(small64.weno(1, left, lin[2:4]) - (lin[2] if left else lin[3])) == 0.0
+
+
+def test_weno_ideal_weights(small64):
+    # constant smoothness source => tau = 0 => alpha = C = (3/10, 3/5, 1/10): the 5th-order linear scheme
+    rng = np.random.default_rng(0)
+    q = rng.standard_normal(6)
+    s = np.ones(6)
+    left = (2 * q[0] - 13 * q[1] + 47 * q[2] + 27 * q[3] - 3 * q[4]) / 60
+    right = (2 * q[5] - 13 * q[4] + 47 * q[3] + 27 * q[2] - 3 * q[1]) / 60
+    assert abs(small64.weno(3, True, q, s) - left) < 1e-13
+    assert abs(small64.weno(3, False, q, s) - right) < 1e-13
+    # WENO3: C = (2/3, 1/3): (-q[n-2] + 5 q[n-1] + 2 q[n]) / 6
+    q4 = q[1:5]
+    assert abs(small64.weno(2, True, q4, np.ones(4)) - (-q4[0] + 5 * q4[1] + 2 * q4[2]) / 6) < 1e-13
+    assert abs(small64.weno(2, False, q4, np.ones(4)) - (-q4[3] + 5 * q4[2] + 2 * q4[1]) / 6) < 1e-13
+    # VelocityStencil: two constant sources are as good as one
+    assert abs(small64.weno(3, True, q, s, 2 * s) - left) < 1e-13
+
+
+def test_weno_is_essentially_non_oscillatory(small64):
+    step = np.array([0.0, 0.0, 0.0, 1.0, 1.0, 1.0])
+    assert abs(small64.weno(3, True, step) - 0.0) < 1e-6      # upwind side is smooth: stays at 0
+    assert abs(small64.weno(3, False, step) - 1.0) < 1e-6
+    # odd symmetry used by the direction-swapped momentum kernel: R(-q) = -R(q)
+    q = np.random.default_rng(1).standard_normal(6)
+    assert small64.weno(3, True, -q) == -small64.weno(3, True, q)
+
+
+def test_split_explicit_weights():
+    frac, w = averaging_weights(30)
+    assert frac == pytest.approx(2 / 30)
+    assert len(w) == 21 and abs(w.sum() - 1) < 1e-14
+    assert (w[:4] < 0).all() and (w[4:] > 0).all()
+    expect = [-0.00276163, -0.00386291, -0.00330547, -0.0010957, 0.00274978, 0.00819649, 0.01518218, 0.02360484,
+              0.03330843, 0.04406644, 0.05556331, 0.06737363, 0.0789391, 0.08954336, 0.09828464, 0.10404618,
+              0.10546443, 0.10089519, 0.08837738, 0.0655948, 0.02983553]
+    assert np.allclose(w, expect, atol=5e-9)
+    assert len(averaging_weights(32)[1]) == 23 and len(averaging_weights(70)[1]) == 50
+
+
+def test_exponential_z_faces_and_vertical_halos():
+    zf = grids.exponential_z_faces(10, 4000.0, 30.0)
+    assert zf[0] == -4000.0 and zf[-1] == 0.0 and (np.diff(zf) > 0).all()
+    g = grids.simple_latitude_longitude_grid(16, 8, 10)
+    z = g.z
+    k = lambda kk: kk + g.Hz - 1
+    assert z["z_f"][k(1)] == -4000.0 and z["z_f"][k(11)] == 0.0
+    assert np.allclose(z["dz_c"][k(1):k(11)], np.diff(zf))
+    assert np.isclose(z["z_f"][k(0)], zf[0] - (zf[1] - zf[0]))                 # linear extrapolation
+    assert np.isclose(z["dz_f"][k(11)], z["z_c"][k(11)] - z["z_c"][k(10)])
+
+
+def test_latlon_metrics_sum_to_sphere_band():
+    g = grids.simple_latitude_longitude_grid(64, 32, 4)
+    az = g.metrics["az_cc"][g.Hy:g.Hy + g.Ny, g.Hx:g.Hx + g.Nx]
+    band = 2 * np.pi * grids.R_EARTH ** 2 * (np.sin(np.deg2rad(80)) - np.sin(np.deg2rad(-80)))
+    assert np.isclose(az.sum(), band, rtol=1e-12)
+
+
+def test_tripolar_grid_fold_symmetry_and_area():
+    g = grids.gaussian_islands_tripolar_grid(64, 32, 6)
+    Nx, Ny, Hx, Hy = g.Nx, g.Ny, g.Hx, g.Hy
+    cc = g.metrics["az_cc"]
+    I = lambda i: i + Hx - 1
+    J = lambda j: j + Hy - 1
+    for i in (1, 5, 40, 64):
+        assert cc[J(Ny + 2), I(i)] == cc[J(Ny - 2), I(Nx - i + 1)]
+        assert np.isclose(cc[J(Ny), I(i)], cc[J(Ny), I(Nx - i + 1)], rtol=1e-9)    # duplicated fold row
+    assert (g.metrics["dx_fc"] > 0).all() and (g.metrics["dy_cf"] > 0).all()
+    # total area of the ocean cap: rows 1..Ny-1 plus half of the duplicated row Ny = sphere north of 80S
+    az = cc[Hy:Hy + Ny, Hx:Hx + Nx]
+    area = az[:-1].sum() + 0.5 * az[-1].sum()
+    cap = 2 * np.pi * grids.R_EARTH ** 2 * (1 - np.sin(np.deg2rad(-80)))
+    assert np.isclose(area, cap, rtol=2e-2)
+    # the poles sit under the islands
+    assert g.bottom_height.max() > 0
+
+
+def test_rest_state_has_zero_tendencies(oracle_mod):
+    g = grids.simple_latitude_longitude_grid(32, 16, 8)
+    m = oracle_mod.OracleModel(oracle_mod.CPUOracle(np.float64), g)
+    zc = g.zc_interior()[:, None, None]
+    M.set(m, T=20 + 5e-3 * zc + 0 * m.interior("T"), S=35 - 1e-3 * zc + 0 * m.interior("S"))
+    M.update_state(m)
+    for n in ("Gn_u", "Gn_T", "Gn_S"):
+        assert np.abs(m.interior(n)).max() == 0.0
+    # row j=1 of Gv is the south wall: it sees p(i,0,k), built from the unfilled y-z halo corner of T,S
+    # (fill order of SURVEY.md A.5) — a quirk with no dynamical effect (v[j=1] is reset to 0 by the BC)
+    assert np.abs(m.interior("Gn_v")[:, 1:g.Ny]).max() < 1e-12
+    assert np.abs(m.interior("w")).max() == 0.0
+
+
+def _fill_index_valued(m, name):
+    p = m.parent(name)
+    p[...] = np.arange(p.size, dtype=np.float64).reshape(p.shape) + 1
+    m.set_parent(name, p)
+
+
+@pytest.mark.parametrize("grid_type", ["simple_lat_lon", "gaussian_islands"])
+def test_halo_fill_properties(oracle_mod, grid_type):
+    m = M.baroclinic_instability_model(oracle_mod.CPUOracle(np.float64), 32, 16, 6, Δt=1.0, grid_type=grid_type,
+                                       model_cls=oracle_mod.OracleModel)
+    g = m.grid
+    for n in ("u", "v", "T", "S", "eta", "U", "V"):
+        _fill_index_valued(m, n)
+    M.tupled_fill_halo_regions_workload(m)
+    Hx, Hy, Hz, Nx, Ny, Nz = g.Hx, g.Hy, g.Hz, g.Nx, g.Ny, g.Nz
+    for n in ("u", "v", "T", "S"):
+        p = m.parent(n)
+        # periodic x over the whole parent
+        assert (p[:, :, :Hx] == p[:, :, Nx:Nx + Hx]).all() and (p[:, :, Nx + Hx:] == p[:, :, Hx:2 * Hx]).all()
+        # idempotent
+        M.tupled_fill_halo_regions_workload(m)
+        assert (m.parent(n) == p).all()
+    T = m.parent("T")
+    for k in range(1, Hz + 1):      # no-flux mirror in z over the interior columns
+        assert (T[Hz - k, Hy:Hy + Ny, Hx:Hx + Nx] == T[Hz + k - 1, Hy:Hy + Ny, Hx:Hx + Nx]).all()
+    v = m.parent("v")
+    assert (v[Hz:Hz + Nz, Hy, Hx:Hx + Nx] == 0).all()                  # impenetrable south wall
+    if g.topo_y == grids.TOPO_FOLD:
+        u = m.parent("u")
+        kk = slice(Hz, Hz + Nz)
+        for mm in (1, 3, 8):
+            for i in (2, 7, 20):
+                assert (T[kk, Ny + mm + Hy - 1, i + Hx - 1] == T[kk, Ny - mm + Hy - 1, Nx - i + 1 + Hx - 1]).all()
+                assert (v[kk, Ny + mm + Hy - 1, i + Hx - 1] == -v[kk, Ny - mm + 1 + Hy - 1, Nx - i + 1 + Hx - 1]).all()
+                assert (u[kk, Ny + mm + Hy - 1, i + Hx - 1] == -u[kk, Ny - mm + Hy - 1, Nx - i + 2 + Hx - 1]).all()
+            # Face-x element whose partner wraps past Nx keeps its sign (zipper quirk)
+            assert (u[kk, Ny + mm + Hy - 1, Hx] == u[kk, Ny - mm + Hy - 1, Hx]).all()
+    else:
+        assert (v[Hz:Hz + Nz, Ny + Hy, Hx:Hx + Nx] == 0).all()         # impenetrable north wall (face Ny+1)
+        for mm in (1, 8):
+            assert (T[Hz:Hz + Nz, Ny + mm + Hy - 1, Hx:Hx + Nx] == T[Hz:Hz + Nz, Ny - mm + Hy, Hx:Hx + Nx]).all()
+
+
+@pytest.mark.parametrize("grid_type", ["simple_lat_lon", "gaussian_islands"])
+def test_discrete_conservation_identities(oracle_mod, grid_type):
+    """(i) the barotropic substeps conserve sum(Az*eta); (ii) tracer fluxes telescope:
+    sum(V*Gc) = -sum(Az * w_top * c_top) because the linear free surface lets tracer through the lid."""
+    m = M.baroclinic_instability_model(oracle_mod.CPUOracle(np.float64), 48, 24, 8, Δt=30.0, grid_type=grid_type,
+                                       model_cls=oracle_mod.OracleModel)
+    g = m.grid
+    rng = np.random.default_rng(3)
+    M.set_baroclinic_instability(m)
+    M.set(m, u=1e-2 * rng.standard_normal(m.interior("u").shape), v=1e-2 * rng.standard_normal(m.interior("v").shape))
+    M.initialize(m)
+    M.update_state(m)
+    az = np.float32(g.metrics["az_cc"]).astype(np.float64)[g.Hy:g.Hy + g.Ny, g.Hx:g.Hx + g.Nx]
+    if g.topo_y == grids.TOPO_FOLD:
+        wrow = np.ones(g.Ny); wrow[-1] = 0.5
+        # row Ny is duplicated across the fold: it is conserved only in the symmetric sense
+        az = az * wrow[:, None]
+    dz = np.float32(g.z["dz_c"]).astype(np.float64)[g.Hz:g.Hz + g.Nz]
+    GT = m.interior("Gn_T")
+    w = m.interior("w")
+    T = m.interior("T")
+    lhs = (GT * az[None] * dz[:, None, None]).sum()
+    rhs = -(az * w[-1] * T[-1]).sum()
+    if g.topo_y == grids.TOPO_BOUNDED:
+        assert abs(lhs - rhs) <= 1e-9 * max(abs(lhs), abs(rhs), (np.abs(GT) * az[None] * dz[:, None, None]).sum())
+        eta0 = (m.interior("eta")[0] * az).sum()
+        M.ab2_step_workload(m, 30.0)
+        eta1 = (m.interior("eta")[0] * az).sum()
+        scale = (np.abs(m.interior("eta")[0]) * az).sum()
+        assert scale > 0 and abs(eta1 - eta0) <= 1e-10 * scale
+    else:
+        # on the folded grid the random state is not fold-symmetric, so only check finiteness + mask
+        assert np.isfinite(GT).all()
+        kb = m.kbot()[g.Hy:g.Hy + g.Ny, g.Hx:g.Hx + g.Nx]
+        solid = np.arange(1, g.Nz + 1)[:, None, None] <= kb[None]
+        assert solid.any() and (m.interior("T")[solid] == 0).all() and (m.interior("u")[solid] == 0).all()
+
+
+def test_float_and_double_oracles_agree(oracle_mod):
+    """Float32 arithmetic (what the product computes in) stays within the reference tolerance of Float64."""
+    ms = []
+    for dt_ in (np.float32, np.float64):
+        m = M.baroclinic_instability_model(oracle_mod.CPUOracle(dt_), 48, 24, 8, Δt=60.0, model_cls=oracle_mod.OracleModel)
+        rng = np.random.default_rng(42)
+        M.set_baroclinic_instability(m)
+        M.set(m, u=1e-3 * rng.random(m.interior("u").shape), v=1e-3 * rng.random(m.interior("v").shape))
+        M.first_time_step(m)
+        for _ in range(3):
+            M.time_step(m)
+        ms.append(m)
+    assert M.compare_states(ms[0], ms[1], include_halos=True, verbose=False)
