@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of libgb25cuda: Float32 cell-steps/s of the GB-25 baroclinic-instability
+HydrostaticFreeSurfaceModel time step (BASELINE.json metric), one process per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the oracle on the host cores)
+
+A "step" is one GordonBell25.time_step! (one AB2 step incl. 21 barotropic substeps and update_state!).
+N = 1 workload: BASELINE.json configs[1] — TripolarGrid 1/4 degree (1440x600x50), gaussian-islands
+bathymetry, Float32.  N > 1: the same 1440x600x50 tile per GPU (weak scaling), domain partitioned in x/y
+with (Rx, Ry) = factors(N) (/root/reference/src/sharding_utils.jl:39-62).
+
+Prints ONE JSON line (rank 0).  `value` = whole-job cell-steps/s with the state resident in HBM;
+`e2e` = the same metric when every step round-trips the prognostic state through host buffers over the
+C ABI (gb25_set_field / gb25_time_step / gb25_get_field); `roofline` = the dominant kernel against the
+measured HBM peak; `cpu_baseline` = the CPU oracle on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (grid_type, Nx, Ny, Nz, dt)
+    "tripolar_quarter_degree": ("gaussian_islands", 1440, 600, 50, 60.0),
+    "latlon_128x64x8": ("simple_lat_lon", 128, 64, 8, 60.0),
+}
+ALGORITHMIC_BYTES_PER_CELL_STEP = 104     # 26 Float32 words of compulsory 3-D traffic
+# algorithmic bytes per cell of one launch of each tendency kernel (DESIGN.md "kernels")
+KERNEL_BYTES_PER_CELL = {"momentum_tendencies": 2 * (4 + 1) * 4,   # two launches: read u,v,w,p, write G
+                         "tracer_tendencies": (5 + 2) * 4}         # read u,v,w,T,S, write GT,GS
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_state(model, seed=42):
+    """Synthetic baroclinic-instability state: T, S of set_baroclinic_instability_kernel!
+    (/root/reference/src/model_utils.jl:99-110) and u, v = 1e-3*U[0,1)
+    (/root/reference/correctness/correctness_baroclinic_instability_simulation_run.jl:40-42)."""
+    from gb25_b200 import model as M
+    M.set_baroclinic_instability(model)
+    rng = np.random.default_rng(seed)
+    shp = model.interior("u").shape
+    M.set(model, u=(1e-3 * rng.random(shp, dtype=np.float32)), v=(1e-3 * rng.random(model.interior("v").shape, dtype=np.float32)))
+
+
+def run_reference_arm(args, workload):
+    """--impl reference: the reference's CPU implementation of the path.  Oceananigans CPU() cannot run here
+    (no Julia in the image), so this is the CPU oracle port with all host threads, on a bounded
+    sample of the same workload (a reduced-size tile of the same grid family and vertical resolution)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gb25_b200 import model as M
+    from oracle import oracle as O
+    O.build()
+    grid_type, Nx, Ny, Nz, dt = WORKLOADS[workload]
+    sx, sy = (4, 4) if Nx >= 512 else (1, 1)
+    nx, ny = Nx // sx, Ny // sy
+    cores = os.cpu_count() or 1
+    m = M.baroclinic_instability_model(O.CPUOracle(np.float32), nx, ny, Nz, Δt=dt * sx, grid_type=grid_type,
+                                       model_cls=O.OracleModel)
+    synthetic_state(m)
+    M.first_time_step(m)
+    for _ in range(max(args.warmup - 1, 0)):
+        M.time_step(m)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        M.time_step(m)
+    el = time.perf_counter() - t0
+    cells = nx * ny * Nz
+    val = cells * args.steps / el
+    sample = f"{grid_type} {nx}x{ny}x{Nz} ({args.steps} steps; 1/{sx * sy} of the {Nx}x{Ny}x{Nz} workload), OpenMP"
+    line = {"impl": "reference", "metric": "cell_steps_per_s", "value": val, "unit": "cell-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "grid": grid_type, "Nx": Nx, "Ny": Ny, "Nz": Nz, "dt": dt},
+            "cpu_baseline": {"value": val, "unit": "cell-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(workload, budget_s=20.0):
+    from gb25_b200 import model as M
+    from oracle import oracle as O
+    O.build()
+    grid_type, Nx, Ny, Nz, dt = WORKLOADS[workload]
+    sx = 4 if Nx >= 512 else 1
+    nx, ny = Nx // sx, Ny // sx
+    m = M.baroclinic_instability_model(O.CPUOracle(np.float32), nx, ny, Nz, Δt=dt * sx, grid_type=grid_type,
+                                       model_cls=O.OracleModel)
+    synthetic_state(m)
+    M.first_time_step(m)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        M.time_step(m)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 50:
+            break
+    return {"value": nx * ny * Nz * n / el, "unit": "cell-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"CPU oracle (C++/OpenMP restatement, not Oceananigans: no Julia in the image) on {grid_type} "
+                      f"{nx}x{ny}x{Nz}, {n} steps in {el:.1f} s"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="tripolar_quarter_degree", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args, args.workload)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import gb25_b200  # noqa: F401
+    from gb25_b200 import model as M, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libgb25cuda has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    grid_type, Nx, Ny, Nz, dt = WORKLOADS[args.workload]
+    Rx, Ry = sharding.factors(world)
+
+    if world > 1:
+        from gb25_b200 import distributed as D
+        model = D.sharded_baroclinic_instability_model(M.B200(local_rank), Nx, Ny, Nz, Δt=dt, grid_type=grid_type,
+                                                       Rx=Rx, Ry=Ry, rank=rank, dist=dist)
+    else:
+        model = M.baroclinic_instability_model(M.B200(local_rank), Nx, Ny, Nz, Δt=dt, grid_type=grid_type)
+    synthetic_state(model, seed=42 + rank)
+    M.first_time_step(model)
+    for _ in range(args.warmup - 1):
+        M.time_step(model)
+    model.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        model.synchronize()
+
+    # ---- timed region: K steps, state resident in HBM, CUDA events on the launching stream
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = model.handle.launch_count()
+    model.handle.call("gb25_enable_stage_timers", 1)
+    barrier()
+    M.loop(model, args.steps)
+    model.synchronize()
+    secs = model.handle.last_loop_seconds()
+    barrier()
+    stages = model.handle.stage_times()
+    model.handle.call("gb25_enable_stage_timers", 0)
+    launches = model.handle.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([secs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    cells_per_rank = Nx * Ny * Nz
+    value = cells_per_rank * world * args.steps / secs
+    # sanity: the run must still be finite
+    eta = model.interior("eta")
+    finite = bool(np.isfinite(eta).all())
+
+    # ---- e2e: every step round-trips the prognostic state through pinned host buffers over the C ABI
+    e2e = None
+    if not args.no_e2e:
+        names = ("u", "v", "T", "S", "eta", "U", "V")
+        host = {}
+        for n in names:
+            shp = model.handle.field_shape(n)
+            tns = torch.empty(shp, dtype=torch.float32, pin_memory=True)
+            host[n] = tns.numpy()
+            model.handle.get_field(n, host[n])
+        nb = sum(a.nbytes for a in host.values())
+        ksteps = max(3, min(args.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            for n in names:
+                model.handle.set_field(n, host[n])
+            M.time_step(model)
+            for n in names:
+                model.handle.get_field(n, host[n])
+        barrier()
+        el = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([el], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        e2e = {"value": cells_per_rank * world * ksteps / el, "unit": "cell-steps/s", "h2d_bytes_per_step": nb,
+               "d2h_bytes_per_step": nb, "steps": ksteps,
+               "protocol": "per step: gb25_set_field(u,v,T,S,eta,U,V) from pinned host, gb25_time_step, gb25_get_field of the same"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    hbm, peak_src = measured_peaks()
+    # dominant kernel = the stage with the largest share of the step
+    tot_ms = sum(ms for ms, _ in stages.values()) or 1.0
+    dom = max((k for k in stages if k in KERNEL_BYTES_PER_CELL), key=lambda k: stages[k][0], default=None)
+    roofline = None
+    if dom:
+        ms, calls = stages[dom]
+        per_call_s = ms * 1e-3 / max(calls, 1)
+        achieved = KERNEL_BYTES_PER_CELL[dom] * cells_per_rank / per_call_s / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                    "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": per_call_s * 1e3, "share_of_step": ms / tot_ms,
+                    "whole_step": {"algorithmic_bytes_per_cell_step": ALGORITHMIC_BYTES_PER_CELL_STEP,
+                                   "achieved": ALGORITHMIC_BYTES_PER_CELL_STEP * value / world / 1e9,
+                                   "frac": ALGORITHMIC_BYTES_PER_CELL_STEP * value / world / 1e9 / hbm},
+                    "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()}}
+    line = {"metric": "cell_steps_per_s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "grid": grid_type, "Nx_per_gpu": Nx, "Ny_per_gpu": Ny, "Nz": Nz, "dt": dt,
+                       "partition": [Rx, Ry], "halo": 8, "substeps": 30, "l2": "inputs larger than L2 (each 3-D field is 226 MB)"
+                       if Nx * Ny * Nz * 4 > 126e6 else "working set fits in L2: latency-bound config",
+                       "state_finite": finite},
+            "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample(args.workload)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
