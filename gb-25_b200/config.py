@@ -24,3 +24,6 @@ class PhysicsConfig:
     south_inactive: int = 1         # U4: tripolar: cells south of j=1 are outside the domain
     cond_diff: int = 1              # U15: immersed-aware differences in ζ and ∇p
     eos_r0: int = 0                 # U8: include r0(z) in ρ′
+    # test-side only: which smoothness-indicator form the CPU checker evaluates (0 = expanded, the recalled
+    # reference form; 1 = sum of squares, the form libgb25cuda always uses — DESIGN.md deviation D1)
+    oracle_beta_form: int = 0

@@ -118,12 +118,26 @@ __global__ void k_mask_fields(DevGrid g, float* u, float* v, float* T, float* S)
   if (T && c0) T[q3] = 0.f;
   if (S && c0) S[q3] = 0.f;
 }
+// barotropic transports (decision U11): masked where the surface-level velocity node is peripheral
+__global__ void k_mask_barotropic(DevGrid g, float* U, float* V) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.Nx) return;
+  const int q2 = id2(g, i, j);
+  const bool c0 = inactive_cell(g, i, j, g.Nz);
+  if (c0 || inactive_cell(g, i - 1, j, g.Nz)) U[q2] = 0.f;
+  if (c0 || inactive_cell(g, i, j - 1, g.Nz)) V[q2] = 0.f;
+}
 void launch_mask(Handle* h, bool uv_only) {
   if (!h->g.immersed) return;
   const DevGrid& g = h->g;
   dim3 b(128), gr((g.Nx + 127) / 128, g.Ny, g.Nz);
   k_mask_fields<<<gr, b, 0, h->stream>>>(g, h->f.u, h->f.v, uv_only ? nullptr : h->f.T, uv_only ? nullptr : h->f.S);
   h->count_launch();
+  if (!uv_only) {
+    dim3 g2((g.Nx + 127) / 128, g.Ny);
+    k_mask_barotropic<<<g2, b, 0, h->stream>>>(g, h->f.bu, h->f.bv);
+    h->count_launch();
+  }
 }
 
 // =====================================================================================

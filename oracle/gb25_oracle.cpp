@@ -45,6 +45,7 @@ struct OConfig {
   int south_inactive;   // U4: RightConnected: cells j<1 count as outside the domain (1) or not (0)
   int cond_diff;        // U15: immersed-aware (conditional) differences in zeta and grad p
   int eos_r0;           // U8: include r0(z) in rho'
+  int beta_form;        // D1: 0 = expanded smoothness indicators (recalled reference form), 1 = sum of squares
   double g, rho0, chi, dtau_frac, weno_eps;
 };
 }
@@ -193,7 +194,12 @@ struct Oracle {
     return 1;
   }
 
-  static inline FT beta3(int r, FT a, FT b, FT cc) {
+  inline FT beta3(int r, FT a, FT b, FT cc) const {
+    if (c.beta_form == 1) {
+      FT d2 = (a - (FT)2 * b) + cc;
+      FT d1 = r == 0 ? ((FT)3 * a - (FT)4 * b) + cc : (r == 1 ? a - cc : (a - (FT)4 * b) + (FT)3 * cc);
+      return (FT)3.25 * d2 * d2 + (FT)0.75 * d1 * d1;
+    }
     switch (r) {
       case 0: return a * ((FT)10 * a - (FT)31 * b + (FT)11 * cc) + b * ((FT)25 * b - (FT)19 * cc) + (FT)4 * cc * cc;
       case 1: return a * ((FT)4 * a - (FT)13 * b + (FT)5 * cc) + b * ((FT)13 * b - (FT)13 * cc) + (FT)4 * cc * cc;
@@ -221,11 +227,12 @@ struct Oracle {
     if (B == 1) return qq[0];
     if (B == 2) {
       // WENO3-Z: S0 = (q1,q2), S1 = (q0,q1)
-      FT b0 = a1[1] * (a1[1] - (FT)2 * a1[2]) + a1[2] * a1[2];
-      FT b1 = a1[0] * (a1[0] - (FT)2 * a1[1]) + a1[1] * a1[1];
+      auto b2f = [&](FT x, FT y) { return c.beta_form == 1 ? (x - y) * (x - y) : x * (x - (FT)2 * y) + y * y; };
+      FT b0 = b2f(a1[1], a1[2]);
+      FT b1 = b2f(a1[0], a1[1]);
       if (s2) {
-        FT c0 = a2[1] * (a2[1] - (FT)2 * a2[2]) + a2[2] * a2[2];
-        FT c1 = a2[0] * (a2[0] - (FT)2 * a2[1]) + a2[1] * a2[1];
+        FT c0 = b2f(a2[1], a2[2]);
+        FT c1 = b2f(a2[0], a2[1]);
         b0 = (b0 + c0) / (FT)2; b1 = (b1 + c1) / (FT)2;
       }
       FT tau = std::fabs(b0 - b1);
@@ -382,9 +389,20 @@ struct Oracle {
         for (int i = 1; i <= Nx; i++)
           if (peripheral(l, i, j, k)) at(f, i, j, k) = 0;
   }
+  // barotropic transports are prognostic fields too (decision U11): masked where the surface-level
+  // velocity node is peripheral, i.e. where the column depth at the node is zero
+  void mask_barotropic() {
+    if (!c.immersed) return;
+    for (int j = 1; j <= Ny; j++)
+      for (int i = 1; i <= Nx; i++) {
+        if (peripheral({1, 0, 0}, i, j, Nz)) at2(F_BU, i, j) = 0;
+        if (peripheral({0, 1, 0}, i, j, Nz)) at2(F_BV, i, j) = 0;
+      }
+  }
   void mask_immersed_fields() {
     mask_field(F_U, {1, 0, 0}); mask_field(F_V, {0, 1, 0});
     mask_field(F_T, {0, 0, 0}); mask_field(F_S, {0, 0, 0});
+    mask_barotropic();
   }
 
   // ------------------------------------------------- compute_w_from_continuity! (row A3)

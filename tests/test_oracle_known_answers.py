@@ -229,3 +229,31 @@ def test_float_and_double_oracles_agree(oracle_mod, state):
         for n in ("u", "v", "w", "T", "S", "eta", "Gn_v", "Gn_T", "Gn_S", "filt_U", "filt_V", "filt_eta"):
             assert M.compare_parent(n, ms[0].parent(n), ms[1].parent(n), rtol=rtol, atol=0, verbose=False), n
         assert M.compare_parent("Gn_u", ms[0].parent("Gn_u"), ms[1].parent("Gn_u"), rtol=2e-2, atol=0, verbose=False)
+
+
+def test_deviation_D1_sum_of_squares_smoothness_is_within_tolerance(oracle_mod):
+    """libgb25cuda evaluates the WENO smoothness indicators as sums of squares (never negative) instead of the
+    expanded polynomial the reference uses; the two forms are algebraically identical.  In Float64 they agree
+    to round-off, and in Float32 the whole model state stays within the reference tolerance."""
+    from gb25_b200.config import PhysicsConfig
+    rng = np.random.default_rng(5)
+    o64 = [oracle_mod.OracleModel(oracle_mod.CPUOracle(np.float64), grids.simple_latitude_longitude_grid(16, 16, 4),
+                                  PhysicsConfig(oracle_beta_form=f)) for f in (0, 1)]
+    for _ in range(50):
+        q = rng.standard_normal(6) * 10 ** rng.uniform(-3, 3)
+        for left in (True, False):
+            a, b = o64[0].weno(3, left, q), o64[1].weno(3, left, q)
+            assert abs(a - b) <= 1e-9 * np.abs(q).max()
+            a, b = o64[0].weno(2, left, q[1:5]), o64[1].weno(2, left, q[1:5])
+            assert abs(a - b) <= 1e-9 * np.abs(q).max()
+    ms = []
+    for f in (0, 1):
+        m = M.baroclinic_instability_model(oracle_mod.CPUOracle(np.float32), 48, 32, 8, Δt=60.0, model_cls=oracle_mod.OracleModel,
+                                           physics=PhysicsConfig(oracle_beta_form=f))
+        r = np.random.default_rng(42)
+        M.set(m, u=1e-3 * r.random(m.interior("u").shape), v=1e-3 * r.random(m.interior("v").shape))
+        M.first_time_step(m)
+        for _ in range(3):
+            M.time_step(m)
+        ms.append(m)
+    assert M.compare_states(ms[0], ms[1], include_halos=True, verbose=False, elementwise=1e-4)
