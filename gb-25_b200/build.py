@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libgb25cuda.so")
-CU_SOURCES = ["gb25_api.cu", "gb25_kernels.cu"]
+CU_SOURCES = ["gb25_api.cu", "gb25_kernels.cu", "gb25_tend_v2.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -43,7 +43,8 @@ def build_cuda(force=False, verbose=False):
     for s in srcs:
         o = s[:-3] + ".o"
         objs.append(o)
-        cmd = [nvcc, *[f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")], "-c", s, "-o", o]
+        cmd = [nvcc, *[f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")],
+               *os.environ.get("GB25_NVCC_DEFINES", "").split(), "-c", s, "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

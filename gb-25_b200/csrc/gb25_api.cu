@@ -251,6 +251,11 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
   const float** dstz[4] = {&g.zf, &g.zc, &g.dzc, &g.dzf};
   for (int a = 0; a < 4; a++) CKC(upload(h, srcz[a], (size_t)g.PZ, dstz[a]));
   CKC(build_immersed_products(h, grid));
+  {
+    const DevGrid* gd = nullptr;
+    CKC(upload(h, &h->g, 1, &gd));
+    h->g_dev = const_cast<DevGrid*>(gd);
+  }
   h->weights.assign(grid->avg_weights, grid->avg_weights + cfg->nsubsteps);
   // fields
   for (int fidx = 0; fidx < GB25_FIELD_COUNT; fidx++) {

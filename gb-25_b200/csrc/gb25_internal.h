@@ -21,6 +21,7 @@ struct StageTimer {
 struct gb25_handle {
   gb25_config cfg;
   DevGrid g;
+  DevGrid* g_dev = nullptr;   // copy of g in device memory (for non-inlined device functions)
   DevFields f;
   cudaStream_t stream = nullptr;
   int device = 0;
@@ -60,6 +61,9 @@ void launch_mask(Handle* h, bool uv_only);
 void launch_compute_w(Handle* h);
 void launch_compute_p(Handle* h);
 void launch_tracer_tendency(Handle* h);
+void launch_tracer_tendency_v1(Handle* h);
+void launch_tracer_tendency_v2(Handle* h);   // gb25_tend_v2.cu
+void launch_momentum_tendency_v1(Handle* h);
 void launch_momentum_tendency(Handle* h);
 void launch_ab2_columns(Handle* h, float dt, float chi);
 void launch_barotropic(Handle* h, float dt);
