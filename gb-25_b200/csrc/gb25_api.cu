@@ -267,6 +267,12 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     CKC(ckcuda(cudaMemsetAsync(d, 0, n * sizeof(float), h->stream), "cudaMemset"));
     h->field_ptr[fidx] = d;
   }
+  for (float** sp : {&h->zeta, &h->dxU, &h->dyV}) {
+    cudaError_t ce = cudaMalloc(sp, n3 * sizeof(float));
+    if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc scratch: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
+    h->allocs.push_back(*sp);
+    CKC(ckcuda(cudaMemsetAsync(*sp, 0, n3 * sizeof(float), h->stream), "cudaMemset"));
+  }
   DevFields& f = h->f;
   f.u = h->field_ptr[GB25_U]; f.v = h->field_ptr[GB25_V]; f.w = h->field_ptr[GB25_W];
   f.T = h->field_ptr[GB25_T]; f.S = h->field_ptr[GB25_S]; f.p = h->field_ptr[GB25_P];
@@ -344,7 +350,8 @@ static void fill_prognostic(Handle* h) {
 }
 static void stage_mask(Handle* h) { StageScope t(h, "mask_immersed_fields"); launch_mask(h, false); }
 static void stage_aux(Handle* h) {
-  { StageScope t(h, "compute_w_from_continuity"); launch_compute_w(h); }
+  if (h->use_fused && h->g.Nx % 2 == 0) { StageScope t(h, "compute_w_from_continuity"); launch_aux_columns(h); }
+  else { StageScope t(h, "compute_w_from_continuity"); launch_compute_w(h); }
   { StageScope t(h, "update_hydrostatic_pressure"); launch_compute_p(h); }
 }
 static void stage_tend(Handle* h) {

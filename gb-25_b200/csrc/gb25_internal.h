@@ -28,6 +28,8 @@ struct gb25_handle {
   std::vector<float> weights;
   std::vector<void*> allocs;
   float* field_ptr[GB25_FIELD_COUNT];
+  // scratch 3-D arrays shared by the v2 kernels: vorticity (F,F,C), delta_x(Ax u) and delta_y(Ay v) at (C,C,C)
+  float *zeta = nullptr, *dxU = nullptr, *dyV = nullptr;
   // clock (model.clock)
   double time = 0.0;
   long iteration = 0;
@@ -64,6 +66,8 @@ void launch_tracer_tendency(Handle* h);
 void launch_tracer_tendency_v1(Handle* h);
 void launch_tracer_tendency_v2(Handle* h);   // gb25_tend_v2.cu
 void launch_momentum_tendency_v1(Handle* h);
+void launch_momentum_tendency_v2(Handle* h);  // gb25_tend_v2.cu
+void launch_aux_columns(Handle* h);           // gb25_tend_v2.cu: w + zeta + flux divergences in one column pass
 void launch_momentum_tendency(Handle* h);
 void launch_ab2_columns(Handle* h, float dt, float chi);
 void launch_barotropic(Handle* h, float dt);

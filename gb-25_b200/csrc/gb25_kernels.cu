@@ -235,7 +235,10 @@ void launch_momentum_tendency_v1(Handle* h) {
   k_momentum_tendency<1><<<gr, b, 0, h->stream>>>(g, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[1]); h->count_launch();
 }
 
-void launch_momentum_tendency(Handle* h) { launch_momentum_tendency_v1(h); }
+void launch_momentum_tendency(Handle* h) {
+  if (h->use_fused && h->g.Nx % 2 == 0) launch_momentum_tendency_v2(h);
+  else launch_momentum_tendency_v1(h);
+}
 
 // =====================================================================================
 // ab2_step! part 1 (rows A8 + A9): barotropic forcing column integral fused with the AB2 update

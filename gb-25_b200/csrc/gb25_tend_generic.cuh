@@ -120,7 +120,8 @@ static __device__ __noinline__ float tracer_cell_generic1(const DevGrid* __restr
 // =====================================================================================
 template <int DIR>
 __device__ __forceinline__ float momentum_G(const DevGrid& g, const float* __restrict__ own, const float* __restrict__ oth,
-                                            const float* __restrict__ w, const float* __restrict__ p, int i, int j, int k) {
+                                            const float* __restrict__ w, const float* __restrict__ p, int i, int j, int k,
+                                            float* wtop = nullptr) {
   const int PX = g.PX, n2 = g.n2;
   const int sO = DIR == 0 ? 1 : PX, sC = DIR == 0 ? PX : 1;
   const float* __restrict__ M1 = DIR == 0 ? g.dxfc : g.dycf;  // own-direction spacing at the own-velocity point
@@ -221,6 +222,7 @@ __device__ __forceinline__ float momentum_G(const DevGrid& g, const float* __res
     const float oR = recon_mem(O + (size_t)e * n2, n2, Bz, wt > 0.f, eps);
     Wf[e] = masked ? 0.f : wt * oR;
   }
+  if (wtop) *wtop = Wf[1];   // (masked) vertical momentum flux through the top face, for k-marching callers
   const float Vterm = (1.f / (AZo[q2] * dz)) * (Phi + (Wf[1] - Wf[0]));
 
   // ---------------- Coriolis (enstrophy conserving, optionally active-cell weighted)

@@ -163,3 +163,367 @@ void launch_tracer_tendency_v2(Handle* h) {
   k_tracer_tendency_v2<NC><<<gr, b, 0, h->stream>>>(g, h->g_dev, h->f.u, h->f.v, h->f.w, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3]);
   h->count_launch();
 }
+
+// =====================================================================================
+// Fused auxiliary column pass: compute_w_from_continuity! (row A3) plus the by-products the momentum kernel
+// would otherwise recompute 12 times per value: the horizontal flux differences dxU = delta_x(Ax u),
+// dyV = delta_y(Ay v) at (C,C,C) and the vertical vorticity zeta at (F,F,C), with the immersed-aware
+// (conditional) differences already applied.  One thread per column of the extended range, marching k.
+// =====================================================================================
+__global__ void __launch_bounds__(128) k_aux_columns(DevGrid g, const float* __restrict__ u, const float* __restrict__ v,
+                                                     float* __restrict__ w, float* __restrict__ zeta, float* __restrict__ dxU,
+                                                     float* __restrict__ dyV) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + (-g.Hx + 2);
+  const int j = blockIdx.y + (-g.Hy + 2);
+  if (i > g.Nx + g.Hx - 1) return;
+  const int q2 = id2(g, i, j), PX = g.PX, n2 = g.n2;
+  const float dyE = g.dyfc[q2 + 1], dyW = g.dyfc[q2], dxN = g.dxcf[q2 + PX], dxS = g.dxcf[q2];
+  const float az = g.azcc[q2];
+  // vorticity metrics and conditional-difference thresholds
+  const float zyE = g.dycf[q2], zyW = g.dycf[q2 - 1], zxN = g.dxfc[q2], zxS = g.dxfc[q2 - PX], azff = g.azff[q2];
+  int t1 = -1, t2 = -1;
+  if (g.immersed && g.cond_diff) {
+    const int c00 = y_outside(g, j) ? GB25_BIG : (int)g.kb[q2], c0m = y_outside(g, j - 1) ? GB25_BIG : (int)g.kb[q2 - PX];
+    const int cm0 = y_outside(g, j) ? GB25_BIG : (int)g.kb[q2 - 1], cmm = y_outside(g, j - 1) ? GB25_BIG : (int)g.kb[q2 - PX - 1];
+    t1 = max(min(c00, c0m), min(cm0, cmm));   // delta_x(dy v) vanishes for k <= t1 (an inactive v node on either side)
+    t2 = max(min(c00, cm0), min(c0m, cmm));   // delta_y(dx u) vanishes for k <= t2
+  }
+  size_t q3 = q2 + (size_t)n2 * g.Hz;  // k = 1
+  float wk = 0.f;
+  w[q3] = 0.f;
+  for (int k = 1; k <= g.Nz; k++, q3 += n2) {
+    const float dz = g.dzc[k + g.Hz - 1];
+    const float u0 = u[q3], v0 = v[q3];
+    const float dU = dyE * dz * u[q3 + 1] - dyW * dz * u0;
+    const float dV = dxN * dz * v[q3 + PX] - dxS * dz * v0;
+    dxU[q3] = dU; dyV[q3] = dV;
+    wk = wk - (dU + dV) / az;
+    w[q3 + n2] = wk;
+    float d1 = zyE * v0 - zyW * v[q3 - 1];
+    float d2 = zxN * u0 - zxS * u[q3 - PX];
+    if (k <= t1) d1 = 0.f;
+    if (k <= t2) d2 = 0.f;
+    zeta[q3] = (d1 - d2) / azff;
+  }
+}
+void launch_aux_columns(Handle* h) {
+  const DevGrid& g = h->g;
+  const int nx = g.Nx + 2 * g.Hx - 2, ny = g.Ny + 2 * g.Hy - 2;
+  dim3 b(128), gr((nx + 127) / 128, ny);
+  k_aux_columns<<<gr, b, 0, h->stream>>>(g, h->f.u, h->f.v, h->f.w, h->zeta, h->dxU, h->dyV);
+  h->count_launch();
+}
+
+// =====================================================================================
+// Momentum tendencies, second generation (row A5).  Same arithmetic as momentum_G<DIR> (gb25_tend_generic.cuh)
+// for cells whose stencil is clear of bathymetry and walls; those cells take no masks, no horizontal order
+// reduction and read zeta / dxU / dyV from the scratch arrays of k_aux_columns instead of rebuilding them from
+// u, v and six metric arrays.  NC = 2 consecutive cells in x per thread, k-marching with the vertical momentum
+// flux carried from face to face and the own-velocity column held in a register window.  Everything else falls
+// back to the generic function (not inlined).
+// =====================================================================================
+template <int DIR>
+static __device__ __noinline__ float momentum_G_call(const DevGrid* __restrict__ gp, const float* __restrict__ own,
+                                                     const float* __restrict__ oth, const float* __restrict__ w,
+                                                     const float* __restrict__ p, int i, int j, int k, float* wtop) {
+  return momentum_G<DIR>(*gp, own, oth, w, p, i, j, k, wtop);
+}
+__device__ __forceinline__ float2 ld2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+// load 2*NP consecutive floats starting at an 8-byte aligned address
+template <int NP>
+__device__ __forceinline__ void ldrow(const float* p, float (&o)[2 * NP]) {
+#pragma unroll
+  for (int b = 0; b < NP; b++) { const float2 a = ld2(p + 2 * b); o[2 * b] = a.x; o[2 * b + 1] = a.y; }
+}
+__device__ __forceinline__ float weno5_fs_sel(const float (&q)[6], const float (&s)[6], bool left, float eps) {
+  return left ? weno5_fs(q[0], q[1], q[2], q[3], q[4], s[0], s[1], s[2], s[3], s[4], eps)
+              : weno5_fs(q[5], q[4], q[3], q[2], q[1], s[5], s[4], s[3], s[2], s[1], eps);
+}
+
+// ---- Gu: own direction = x (contiguous), cross = y
+__global__ void __launch_bounds__(128) k_gu_v2(DevGrid g, const DevGrid* __restrict__ gp, const float* __restrict__ u,
+                                               const float* __restrict__ v, const float* __restrict__ w,
+                                               const float* __restrict__ p, const float* __restrict__ zeta,
+                                               const float* __restrict__ dxU, const float* __restrict__ dyV,
+                                               float* __restrict__ G) {
+  constexpr int NC = 2;
+  const int i0 = NC * (blockIdx.x * blockDim.x + threadIdx.x) + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i0 > g.Nx || j > g.Ny) return;
+  const int PX = g.PX, n2 = g.n2, Nz = g.Nz;
+  const int q2 = id2(g, i0, j);
+  const float eps = g.eps;
+  // ---- hoisted 2-D data
+  float m1[NC], rV0[NC], fbar[NC], mv[2][NC + 1], azw[NC + 3];
+  int kbc[NC], kgen = 0;
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    m1[c] = g.dxfc[q2 + c];
+    rV0[c] = g.azfc[q2 + c];
+    fbar[c] = (g.fff[q2 + c] + g.fff[q2 + c + PX]) * 0.5f;
+    kbc[c] = g.kb[q2 + c];
+    kgen = max(kgen, (int)g.knear[q2 + c] + 1);
+  }
+#pragma unroll
+  for (int c = 0; c <= NC; c++) { mv[0][c] = g.dxcf[q2 + c - 1]; mv[1][c] = g.dxcf[q2 + c - 1 + PX]; }
+#pragma unroll
+  for (int c = 0; c < NC + 3; c++) azw[c] = g.azcc[q2 + c - 2];
+  // ---- vertical register window of u: WU[c][m] = u(i0+c, j, k-3+m)
+  size_t q3 = q2 + (size_t)n2 * g.Hz;
+  float WU[NC][7];
+#pragma unroll
+  for (int m = 0; m < 7; m++) {
+    const float2 a = ld2(u + q3 + (ptrdiff_t)(m - 3) * n2);
+    WU[0][m] = a.x; WU[1][m] = a.y;
+  }
+  float Wb[NC] = {0.f, 0.f};   // carried vertical flux through the bottom face (set by the generic path at k = 1)
+  for (int k = 1; k <= Nz; k++, q3 += n2) {
+    float out[NC];
+    if (k <= kgen) {
+      for (int c = 0; c < NC; c++) {
+        float wt;
+        const float o = momentum_G_call<0>(gp, u, v, w, p, i0 + c, j, k, &wt);
+#pragma unroll
+        for (int cc = 0; cc < NC; cc++) if (cc == c) { out[cc] = o; Wb[cc] = wt; }
+      }
+    } else {
+      const float dz = g.dzc[k + g.Hz - 1];
+      // ---- rows of u (row j: cols i0-4 .. i0+5; rows j-3..j+3: cols i0, i0+1)
+      float ur[10];
+      {
+        float a[4], b[4];
+        ldrow<2>(u + q3 - 4, a); ldrow<2>(u + q3 + 2, b);
+#pragma unroll
+        for (int n = 0; n < 4; n++) { ur[n] = a[n]; ur[6 + n] = b[n]; }
+        ur[4] = WU[0][3]; ur[5] = WU[1][3];
+      }
+      float uy[7][NC];
+#pragma unroll
+      for (int m = 0; m < 7; m++) {
+        if (m == 3) { uy[3][0] = ur[4]; uy[3][1] = ur[5]; continue; }
+        const float2 a = ld2(u + q3 + (m - 3) * PX); uy[m][0] = a.x; uy[m][1] = a.y;
+      }
+      // ---- rows j-2..j+3 of v: cols i0-2 .. i0+1 (col i0-2 unused), and of zeta: cols i0, i0+1
+      float vy[6][4], zy[6][NC];
+#pragma unroll
+      for (int m = 0; m < 6; m++) {
+        ldrow<2>(v + q3 - 2 + (m - 2) * PX, vy[m]);
+        const float2 a = ld2(zeta + q3 + (m - 2) * PX); zy[m][0] = a.x; zy[m][1] = a.y;
+      }
+      // ---- row j of dxU, dyV: cols i0-4 .. i0+3
+      float dxr[8], dyr[8];
+      ldrow<4>(dxU + q3 - 4, dxr); ldrow<4>(dyV + q3 - 4, dyr);
+      // ---- w at the top face, cols i0-2 .. i0+3 (i0+3 unused); p at cols i0-2(unused), i0-1, i0, i0+1
+      float wr[6], pr[4];
+      ldrow<3>(w + q3 + n2 - 2, wr); ldrow<2>(p + q3 - 2, pr);
+      const int Bw = (g.immersed && k + 1 > Nz) ? 1 : 2;
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        const float own0 = ur[4 + c];
+        const bool lown = own0 > 0.f;
+        // vorticity flux: -v^ zeta^R (VelocityStencil smoothness)
+        const float xm0 = mv[0][c] * vy[2][1 + c], xm1 = mv[1][c] * vy[3][1 + c];
+        const float x00 = mv[0][c + 1] * vy[2][2 + c], x01 = mv[1][c + 1] * vy[3][2 + c];
+        const float oavg = ((xm0 + xm1) * 0.5f + (x00 + x01) * 0.5f) * 0.5f;
+        const float ohat = oavg / m1[c];
+        float zq[6], zs[6], zr[6];
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+          zq[m] = zy[m][c];
+          zs[m] = (uy[m][c] + uy[m + 1][c]) * 0.5f;
+          zr[m] = (vy[m][1 + c] + vy[m][2 + c]) * 0.5f;
+        }
+        const float zR = ohat > 0.f ? weno5_vs(zq[0], zq[1], zq[2], zq[3], zq[4], zs[0], zs[1], zs[2], zs[3], zs[4], zr[0], zr[1], zr[2], zr[3], zr[4], eps)
+                                    : weno5_vs(zq[5], zq[4], zq[3], zq[2], zq[1], zs[5], zs[4], zs[3], zs[2], zs[1], zr[5], zr[4], zr[3], zr[2], zr[1], eps);
+        const float Hterm = -ohat * zR;
+        // divergence flux and kinetic-energy gradient along x (cells i-3 .. i+2  <->  dxr[1+c .. 6+c])
+        float dOw[6], dv[6], dK[6], sK[6];
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+          dOw[m] = dxr[1 + c + m];
+          dv[m] = dxr[1 + c + m] + dyr[1 + c + m];
+          const float o0 = ur[1 + c + m], o1 = ur[2 + c + m];
+          dK[m] = o1 * o1 * 0.5f - o0 * o0 * 0.5f;
+          sK[m] = (o0 + o1) * 0.5f;
+        }
+        const float dvs = sym4(dyr[2 + c], dyr[3 + c], dyr[4 + c], dyr[5 + c], 2);
+        const float duR = weno5_fs_sel(dOw, dv, lown, eps);
+        const float Phi = own0 * (dvs + duR);
+        const float dKo = weno5_fs_sel(dK, sK, lown, eps);
+        float kc[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          const float t0 = vy[m + 1][2 + c], tm = vy[m + 1][1 + c];
+          kc[m] = t0 * t0 * 0.5f - tm * tm * 0.5f;
+        }
+        const float Bterm = (dKo + sym4(kc[0], kc[1], kc[2], kc[3], 2)) / m1[c];
+        // vertical advection: top face k+1, bottom face carried
+        const float wt = sym4(azw[c] * wr[c], azw[c + 1] * wr[c + 1], azw[c + 2] * wr[c + 2], azw[c + 3] * wr[c + 3], Bw);
+        const int Bz = zbuf(g, kbc[c], k + 1, 3);
+        const float Wt = wt * weno_sel_B(WU[c][1], WU[c][2], WU[c][3], WU[c][4], WU[c][5], WU[c][6], Bz, wt > 0.f, eps);
+        const float Vterm = (1.f / (rV0[c] * dz)) * (Phi + (Wt - Wb[c]));
+        Wb[c] = Wt;
+        const float cor = -(fbar[c] * oavg / m1[c]);
+        const float dp = (pr[2 + c] - pr[1 + c]) / m1[c];
+        out[c] = -(Hterm + Vterm + Bterm) - cor - dp;
+      }
+    }
+    *reinterpret_cast<float2*>(G + q3) = make_float2(out[0], out[1]);
+    {
+      const float2 a = ld2(u + q3 + (size_t)4 * n2);
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+#pragma unroll
+        for (int m = 0; m < 6; m++) WU[c][m] = WU[c][m + 1];
+      }
+      WU[0][6] = a.x; WU[1][6] = a.y;
+    }
+  }
+}
+
+// ---- Gv: own direction = y, cross = x.  The swapped vorticity of momentum_G<1> is -zeta and the
+// reconstruction is odd, so +u^ zeta^R with zeta from the scratch array is the identical value.
+__global__ void __launch_bounds__(128) k_gv_v2(DevGrid g, const DevGrid* __restrict__ gp, const float* __restrict__ u,
+                                               const float* __restrict__ v, const float* __restrict__ w,
+                                               const float* __restrict__ p, const float* __restrict__ zeta,
+                                               const float* __restrict__ dxU, const float* __restrict__ dyV,
+                                               float* __restrict__ G) {
+  constexpr int NC = 2;
+  const int i0 = NC * (blockIdx.x * blockDim.x + threadIdx.x) + 1;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (i0 > g.Nx || j > g.Ny) return;
+  const int PX = g.PX, n2 = g.n2, Nz = g.Nz;
+  const int q2 = id2(g, i0, j);
+  const float eps = g.eps;
+  // ---- hoisted 2-D data
+  float m1[NC], rV0[NC], fbar[NC], mu[2][NC + 1], azw[4][NC];
+  int kbc[NC], kgen = 0;
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    m1[c] = g.dycf[q2 + c];
+    rV0[c] = g.azcf[q2 + c];
+    fbar[c] = (g.fff[q2 + c] + g.fff[q2 + c + 1]) * 0.5f;
+    kbc[c] = g.kb[q2 + c];
+    kgen = max(kgen, (int)g.knear[q2 + c] + 1);
+#pragma unroll
+    for (int m = 0; m < 4; m++) azw[m][c] = g.azcc[q2 + c + (m - 2) * PX];
+  }
+#pragma unroll
+  for (int c = 0; c <= NC; c++) { mu[0][c] = g.dyfc[q2 + c - PX]; mu[1][c] = g.dyfc[q2 + c]; }
+  // ---- vertical register window of v
+  size_t q3 = q2 + (size_t)n2 * g.Hz;
+  float WV[NC][7];
+#pragma unroll
+  for (int m = 0; m < 7; m++) {
+    const float2 a = ld2(v + q3 + (ptrdiff_t)(m - 3) * n2);
+    WV[0][m] = a.x; WV[1][m] = a.y;
+  }
+  float Wb[NC] = {0.f, 0.f};
+  for (int k = 1; k <= Nz; k++, q3 += n2) {
+    float out[NC];
+    if (k <= kgen) {
+      for (int c = 0; c < NC; c++) {
+        float wt;
+        const float o = momentum_G_call<1>(gp, v, u, w, p, i0 + c, j, k, &wt);
+#pragma unroll
+        for (int cc = 0; cc < NC; cc++) if (cc == c) { out[cc] = o; Wb[cc] = wt; }
+      }
+    } else {
+      const float dz = g.dzc[k + g.Hz - 1];
+      // ---- v: row j cols i0-4 .. i0+5; rows j-3..j+3 cols i0, i0+1
+      float vr[10];
+      {
+        float a[4], b[4];
+        ldrow<2>(v + q3 - 4, a); ldrow<2>(v + q3 + 2, b);
+#pragma unroll
+        for (int n = 0; n < 4; n++) { vr[n] = a[n]; vr[6 + n] = b[n]; }
+        vr[4] = WV[0][3]; vr[5] = WV[1][3];
+      }
+      float vy[7][NC];
+#pragma unroll
+      for (int m = 0; m < 7; m++) {
+        if (m == 3) { vy[3][0] = vr[4]; vy[3][1] = vr[5]; continue; }
+        const float2 a = ld2(v + q3 + (m - 3) * PX); vy[m][0] = a.x; vy[m][1] = a.y;
+      }
+      // ---- u rows j-1, j and zeta row j: cols i0-2 .. i0+5
+      float us[8], un[8], zr8[8];
+      ldrow<4>(u + q3 - 2 - PX, us); ldrow<4>(u + q3 - 2, un); ldrow<4>(zeta + q3 - 2, zr8);
+      // ---- dyV, dxU rows j-3 .. j+2, w (top face) rows j-2 .. j+1, p rows j-1, j: cols i0, i0+1
+      float dyc[6][NC], dxc[6][NC], wc[4][NC], ps[NC], pn[NC];
+#pragma unroll
+      for (int m = 0; m < 6; m++) {
+        const float2 a = ld2(dyV + q3 + (m - 3) * PX), b = ld2(dxU + q3 + (m - 3) * PX);
+        dyc[m][0] = a.x; dyc[m][1] = a.y; dxc[m][0] = b.x; dxc[m][1] = b.y;
+      }
+#pragma unroll
+      for (int m = 0; m < 4; m++) { const float2 a = ld2(w + q3 + n2 + (m - 2) * PX); wc[m][0] = a.x; wc[m][1] = a.y; }
+      { const float2 a = ld2(p + q3 - PX), b = ld2(p + q3); ps[0] = a.x; ps[1] = a.y; pn[0] = b.x; pn[1] = b.y; }
+      const int Bw = (g.immersed && k + 1 > Nz) ? 1 : 2;
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        const float own0 = vr[4 + c];
+        const bool lown = own0 > 0.f;
+        // us/un index n <-> col i0-2+n ; cell i = i0+c  ->  u(i) at n = c+2
+        const float xm0 = mu[0][c] * us[c + 2], xm1 = mu[0][c + 1] * us[c + 3];
+        const float x00 = mu[1][c] * un[c + 2], x01 = mu[1][c + 1] * un[c + 3];
+        const float oavg = ((xm0 + xm1) * 0.5f + (x00 + x01) * 0.5f) * 0.5f;
+        const float ohat = oavg / m1[c];
+        float zq[6], zs[6], zr[6];
+#pragma unroll
+        for (int m = 0; m < 6; m++) {           // window along x: cols i-2 .. i+3
+          zq[m] = zr8[c + m];
+          zs[m] = (vr[1 + c + m] + vr[2 + c + m]) * 0.5f;   // (v(i+b-1, j) + v(i+b, j)) / 2
+          zr[m] = (us[c + m] + un[c + m]) * 0.5f;            // (u(i+b, j-1) + u(i+b, j)) / 2
+        }
+        const float zR = ohat > 0.f ? weno5_vs(zq[0], zq[1], zq[2], zq[3], zq[4], zs[0], zs[1], zs[2], zs[3], zs[4], zr[0], zr[1], zr[2], zr[3], zr[4], eps)
+                                    : weno5_vs(zq[5], zq[4], zq[3], zq[2], zq[1], zs[5], zs[4], zs[3], zs[2], zs[1], zr[5], zr[4], zr[3], zr[2], zr[1], eps);
+        const float Hterm = ohat * zR;
+        float dOw[6], dv[6], dK[6], sK[6];
+#pragma unroll
+        for (int m = 0; m < 6; m++) {           // window along y: rows j-3 .. j+2
+          dOw[m] = dyc[m][c];
+          dv[m] = dxc[m][c] + dyc[m][c];
+          const float o0 = vy[m][c], o1 = vy[m + 1][c];
+          dK[m] = o1 * o1 * 0.5f - o0 * o0 * 0.5f;
+          sK[m] = (o0 + o1) * 0.5f;
+        }
+        const float dus = sym4(dxc[1][c], dxc[2][c], dxc[3][c], dxc[4][c], 2);
+        const float dvR = weno5_fs_sel(dOw, dv, lown, eps);
+        const float Phi = own0 * (dus + dvR);
+        const float dKo = weno5_fs_sel(dK, sK, lown, eps);
+        float kc[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {           // cols i-1 .. i+2
+          const float t0 = un[c + 1 + m], tm = us[c + 1 + m];
+          kc[m] = t0 * t0 * 0.5f - tm * tm * 0.5f;
+        }
+        const float Bterm = (dKo + sym4(kc[0], kc[1], kc[2], kc[3], 2)) / m1[c];
+        const float wt = sym4(azw[0][c] * wc[0][c], azw[1][c] * wc[1][c], azw[2][c] * wc[2][c], azw[3][c] * wc[3][c], Bw);
+        const int Bz = zbuf(g, kbc[c], k + 1, 3);
+        const float Wt = wt * weno_sel_B(WV[c][1], WV[c][2], WV[c][3], WV[c][4], WV[c][5], WV[c][6], Bz, wt > 0.f, eps);
+        const float Vterm = (1.f / (rV0[c] * dz)) * (Phi + (Wt - Wb[c]));
+        Wb[c] = Wt;
+        const float cor = fbar[c] * oavg / m1[c];
+        const float dp = (pn[c] - ps[c]) / m1[c];
+        out[c] = -(Hterm + Vterm + Bterm) - cor - dp;
+      }
+    }
+    *reinterpret_cast<float2*>(G + q3) = make_float2(out[0], out[1]);
+    {
+      const float2 a = ld2(v + q3 + (size_t)4 * n2);
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+#pragma unroll
+        for (int m = 0; m < 6; m++) WV[c][m] = WV[c][m + 1];
+      }
+      WV[0][6] = a.x; WV[1][6] = a.y;
+    }
+  }
+}
+
+void launch_momentum_tendency_v2(Handle* h) {
+  const DevGrid& g = h->g;
+  dim3 b(16, 8), gr((g.Nx / 2 + b.x - 1) / b.x, (g.Ny + b.y - 1) / b.y);
+  k_gu_v2<<<gr, b, 0, h->stream>>>(g, h->g_dev, h->f.u, h->f.v, h->f.w, h->f.p, h->zeta, h->dxU, h->dyV, h->f.gn[0]); h->count_launch();
+  k_gv_v2<<<gr, b, 0, h->stream>>>(g, h->g_dev, h->f.u, h->f.v, h->f.w, h->f.p, h->zeta, h->dxU, h->dyV, h->f.gn[1]); h->count_launch();
+}
