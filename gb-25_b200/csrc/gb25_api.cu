@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <utility>
 
 #include "gb25_internal.h"
 
@@ -273,6 +275,16 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     h->allocs.push_back(*sp);
     CKC(ckcuda(cudaMemsetAsync(*sp, 0, n3 * sizeof(float), h->stream), "cudaMemset"));
   }
+  for (float** sp : {&h->us2, &h->vs2}) {
+    cudaError_t ce = cudaMalloc(sp, n2 * sizeof(float));
+    if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc scratch: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
+    h->allocs.push_back(*sp);
+    CKC(ckcuda(cudaMemsetAsync(*sp, 0, n2 * sizeof(float), h->stream), "cudaMemset"));
+  }
+  {
+    const char* e = getenv("GB25_FUSED");
+    h->use_fused = !(e && e[0] == '0');
+  }
   DevFields& f = h->f;
   f.u = h->field_ptr[GB25_U]; f.v = h->field_ptr[GB25_V]; f.w = h->field_ptr[GB25_W];
   f.T = h->field_ptr[GB25_T]; f.S = h->field_ptr[GB25_S]; f.p = h->field_ptr[GB25_P];
@@ -384,9 +396,34 @@ static void stage_initialize(Handle* h) {
   HaloSpec sb[2] = {{h->f.bu, 1, 0, 0, -1.f}, {h->f.bv, 0, 1, 0, -1.f}};
   launch_fill_halo(h, sb, 2, false);
 }
+// fused step path: identical results, fewer passes over the 3-D state (see gb25_kernels.cu "Fused step path")
+static void one_time_step_fused(Handle* h, float dt, float chi) {
+  DevFields& f = h->f;
+  { StageScope t(h, "ab2_step_fields"); launch_ab2_fused(h, dt, chi); }
+  {
+    StageScope t(h, "split_explicit_free_surface");
+    HaloSpec sg[2] = {{f.gU, 1, 0, 0, -1.f}, {f.gV, 0, 1, 0, -1.f}};
+    launch_fill_halo(h, sg, 2, false);
+    launch_barotropic(h, dt);
+    HaloSpec sb[2] = {{f.bu, 1, 0, 0, -1.f}, {f.bv, 0, 1, 0, -1.f}};
+    launch_fill_halo(h, sb, 2, false);
+  }
+  h->time += (double)dt; h->iteration += 1; h->last_dt = dt;
+  { StageScope t(h, "correct_velocities_and_cache"); launch_correct_fused(h); }
+  // G- <- Gn: swap the buffers; the tendency kernels below overwrite the whole interior of the new Gn,
+  // and the halos of both are identically zero
+  for (int q = 0; q < 4; q++) {
+    std::swap(f.gn[q], f.gm[q]);
+    std::swap(h->field_ptr[GB25_GN_U + q], h->field_ptr[GB25_GM_U + q]);
+  }
+  fill_prognostic(h);
+  stage_aux(h);
+  stage_tend(h);
+}
 static void one_time_step(Handle* h, float dt, bool euler) {
   euler = euler || (dt != h->last_dt);
   const float chi = euler ? -0.5f : h->cfg.chi;
+  if (h->use_fused) { one_time_step_fused(h, dt, chi); return; }
   stage_ab2(h, dt, chi);
   h->time += (double)dt; h->iteration += 1; h->last_dt = dt;
   stage_correct(h);

@@ -30,6 +30,7 @@ struct gb25_handle {
   float* field_ptr[GB25_FIELD_COUNT];
   // scratch 3-D arrays shared by the v2 kernels: vorticity (F,F,C), delta_x(Ax u) and delta_y(Ay v) at (C,C,C)
   float *zeta = nullptr, *dxU = nullptr, *dyV = nullptr;
+  float *us2 = nullptr, *vs2 = nullptr;   // 2-D: column sums of the AB2-updated, masked velocities (fused path)
   // clock (model.clock)
   double time = 0.0;
   long iteration = 0;
@@ -73,3 +74,6 @@ void launch_ab2_columns(Handle* h, float dt, float chi);
 void launch_barotropic(Handle* h, float dt);
 void launch_correct_cache(Handle* h);
 void launch_barotropic_mode(Handle* h);
+void launch_ab2_fused(Handle* h, float dt, float chi);
+void launch_correct_fused(Handle* h);
+void launch_barotropic_substeps(Handle* h, float dt);

@@ -382,3 +382,84 @@ void launch_barotropic_mode(Handle* h) {
   dim3 b(128), gr((g.Nx + 127) / 128, g.Ny);
   k_barotropic_mode<<<gr, b, 0, h->stream>>>(g, h->f); h->count_launch();
 }
+
+// =====================================================================================
+// Fused step path (gb25_time_step / gb25_loop).  Same arithmetic as the operator-level kernels above, with the
+// pointwise stages folded into the two column passes that have to touch the state anyway:
+//   k_ab2_fused     = compute_free_surface_tendency! + ab2_step_velocities!/tracers! + mask_immersed_field!(u,v)
+//                     (done by step_free_surface! after the substeps; it does not interact with them) + the T,S
+//                     mask of the next update_state! + the column sums the corrector needs, and
+//   k_correct_fused = barotropic corrector + mask_immersed_model_fields!(u,v,U,V) of update_state!.
+// G- <- Gn becomes a pointer swap on the host.
+// =====================================================================================
+__global__ void k_ab2_fused(DevGrid g, DevFields f, float* __restrict__ us2, float* __restrict__ vs2, float dt, float chi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.Nx) return;
+  const int q2 = id2(g, i, j), n2 = g.n2;
+  const float c1 = 1.5f + chi, c2 = 0.5f + chi;
+  const float ne = (chi != -0.5f) ? 1.f : 0.f;
+  const int kb0 = g.kb[q2], kbw = g.kb[q2 - 1], kbs = g.kb[q2 - g.PX];
+  const bool ywall = y_outside(g, j) || y_outside(g, j - 1);
+  const bool imm = g.immersed;
+  float su = 0.f, sv = 0.f, bu = 0.f, bv = 0.f;
+  size_t q3 = q2 + (size_t)n2 * g.Hz;
+  for (int k = 1; k <= g.Nz; k++, q3 += n2) {
+    const float dz = g.dzc[k + g.Hz - 1];
+    const float gu = c1 * f.gn[0][q3] - c2 * f.gm[0][q3] * ne;
+    const float gv = c1 * f.gn[1][q3] - c2 * f.gm[1][q3] * ne;
+    const bool pu = k <= kb0 || k <= kbw;
+    const bool pv = ywall || k <= kb0 || k <= kbs;
+    const float tu = dz * (pu ? 0.f : gu), tv = dz * (pv ? 0.f : gv);
+    su = (k == 1) ? tu : su + tu;
+    sv = (k == 1) ? tv : sv + tv;
+    float un = f.u[q3] + dt * gu, vn = f.v[q3] + dt * gv;
+    float Tn = f.T[q3] + dt * (c1 * f.gn[2][q3] - c2 * f.gm[2][q3]);
+    float Sn = f.S[q3] + dt * (c1 * f.gn[3][q3] - c2 * f.gm[3][q3]);
+    if (imm) {
+      if (pu) un = 0.f;
+      if (pv) vn = 0.f;
+      if (k <= kb0) { Tn = 0.f; Sn = 0.f; }
+    }
+    f.u[q3] = un; f.v[q3] = vn; f.T[q3] = Tn; f.S[q3] = Sn;
+    const float wu = dz * un, wv = dz * vn;
+    bu = (k == 1) ? wu : bu + wu;
+    bv = (k == 1) ? wv : bv + wv;
+  }
+  f.gU[q2] = su; f.gV[q2] = sv;
+  us2[q2] = bu; vs2[q2] = bv;
+}
+__global__ void k_correct_fused(DevGrid g, DevFields f, const float* __restrict__ us2, const float* __restrict__ vs2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.Nx) return;
+  const int q2 = id2(g, i, j), n2 = g.n2;
+  const float su = us2[q2], sv = vs2[q2];
+  f.fu[q2] = su; f.fv[q2] = sv;     // filtered_state.U/V are reused as scratch by the reference
+  const float cu = (f.bu[q2] - su) / g.Hfc[q2], cv = (f.bv[q2] - sv) / g.Hcf[q2];
+  const int kb0 = g.kb[q2], kbw = g.kb[q2 - 1], kbs = g.kb[q2 - g.PX];
+  const bool ywall = y_outside(g, j) || y_outside(g, j - 1);
+  const bool imm = g.immersed;
+  size_t q3 = q2 + (size_t)n2 * g.Hz;
+  for (int k = 1; k <= g.Nz; k++, q3 += n2) {
+    float un = f.u[q3] + cu, vn = f.v[q3] + cv;
+    if (imm) {
+      if (k <= kb0 || k <= kbw) un = 0.f;
+      if (ywall || k <= kb0 || k <= kbs) vn = 0.f;
+    }
+    f.u[q3] = un; f.v[q3] = vn;
+  }
+  if (imm) {   // barotropic transports: masked where the surface node is peripheral (decision U11)
+    if (g.Nz <= kb0 || g.Nz <= kbw) f.bu[q2] = 0.f;
+    if (ywall || g.Nz <= kb0 || g.Nz <= kbs) f.bv[q2] = 0.f;
+  }
+  f.gmU[q2] = f.gU[q2]; f.gmV[q2] = f.gV[q2];
+}
+void launch_ab2_fused(Handle* h, float dt, float chi) {
+  const DevGrid& g = h->g;
+  dim3 b(128), gr((g.Nx + 127) / 128, g.Ny);
+  k_ab2_fused<<<gr, b, 0, h->stream>>>(g, h->f, h->us2, h->vs2, dt, chi); h->count_launch();
+}
+void launch_correct_fused(Handle* h) {
+  const DevGrid& g = h->g;
+  dim3 b(128), gr((g.Nx + 127) / 128, g.Ny);
+  k_correct_fused<<<gr, b, 0, h->stream>>>(g, h->f, h->us2, h->vs2); h->count_launch();
+}

@@ -195,3 +195,21 @@ def test_error_behaviour(oracle_mod):
     m.synchronize()
     assert m.handle.last_loop_seconds() > 0 and m.handle.launch_count() > 0
     m.close()
+
+
+@pytest.mark.parametrize("grid_type,Nx,Ny,Nz", GRIDS)
+def test_fused_step_path_equals_operator_path(oracle_mod, monkeypatch, grid_type, Nx, Ny, Nz):
+    """gb25_time_step runs fused kernels (AB2+mask+column sums, corrector+mask, G pointer swap, blocked
+    tendency kernels); GB25_FUSED=0 selects the operator-per-kernel path.  Masks, AB2 and corrector are the
+    same arithmetic (bit-exact); the blocked tendency kernels differ from the per-cell ones only in
+    reciprocal/FMA details, far inside the reference tolerance."""
+    import os
+    rm_f, vm = make_models(grid_type, Nx, Ny, Nz, 60.0, oracle_mod)
+    monkeypatch.setenv("GB25_FUSED", "0")
+    rm_o, _ = make_models(grid_type, Nx, Ny, Nz, 60.0, oracle_mod)
+    monkeypatch.delenv("GB25_FUSED")
+    for m in (rm_f, rm_o):
+        M.first_time_step(m)
+        for _ in range(4):
+            M.time_step(m)
+    assert M.compare_states(rm_f, rm_o, include_halos=True, rtol=2e-5, atol=0.0, verbose=False, elementwise=2e-5)
