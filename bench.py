@@ -208,6 +208,9 @@ def main():
     else:
         model = M.baroclinic_instability_model(M.B200(local_rank), Nx, Ny, Nz, Δt=dt, grid_type=grid_type)
     synthetic_state(model, seed=42 + rank)
+    if dist is not None:
+        from gb25_b200 import distributed as D
+        D.barrier(model)          # uploads must not race with a neighbour's halo pushes
     M.first_time_step(model)
     for _ in range(args.warmup - 1):
         M.time_step(model)
@@ -261,6 +264,8 @@ def main():
         for _ in range(ksteps):
             for n in names:
                 model.handle.set_field(n, host[n])
+            if dist is not None:
+                dist.barrier()    # a tile's upload must be complete before a neighbour pushes halos into it
             M.time_step(model)
             for n in names:
                 model.handle.get_field(n, host[n])

@@ -82,7 +82,7 @@ static void parent_shape(const Handle* h, int field, int shape[3]) {
   const FieldInfo& fi = kFieldInfo[field];
   const gb25_config& c = h->cfg;
   shape[0] = c.Nx + 2 * c.Hx;
-  shape[1] = c.Ny + 2 * c.Hy + ((fi.ly && c.topo_y == GB25_TOPO_BOUNDED) ? 1 : 0);
+  shape[1] = c.Ny + 2 * c.Hy + ((fi.ly && h->g.wall_n) ? 1 : 0);   // Bounded Face-y: N+1 points on the tile that owns the wall
   shape[2] = fi.three_d ? c.Nz + 2 * c.Hz + fi.lz : 1;
 }
 
@@ -127,7 +127,7 @@ static int build_immersed_products(Handle* h, const gb25_grid* grid) {
       kb[q] = (short)k0;
       Hcc[q] = ztop - zf(k0 + 1);
       const int j = J - c.Hy + 1;
-      const bool yout = c.topo_y == GB25_TOPO_BOUNDED ? (j < 1 || j > c.Ny) : (c.south_inactive && j < 1);
+      const bool yout = (h->g.wall_s && j < 1) || (h->g.wall_n && j > c.Ny);
       kbe[q] = yout ? (short)GB25_BIG : (short)k0;
     }
   for (int J = 0; J < PY; J++)
@@ -182,6 +182,7 @@ extern "C" int gb25_destroy(gb25_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->graph) cudaGraphDestroy(h->graph);
+  exchange_close(h);
   for (void* p : h->allocs) cudaFree(p);
   if (h->stage_dev) cudaFree(h->stage_dev);
   for (auto& s : h->timers) for (auto& e : s.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -240,6 +241,8 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
   g.topo_y = cfg->topo_y; g.immersed = cfg->immersed && grid->bottom_height; g.coriolis_scheme = cfg->coriolis_scheme;
   g.fold_variant = cfg->fold_variant; g.south_inactive = cfg->south_inactive; g.cond_diff = cfg->cond_diff; g.eos_r0 = cfg->eos_r0;
   g.g = cfg->g; g.rho0 = cfg->rho0; g.eps = cfg->weno_eps;
+  g.wall_s = (cfg->ry == 0) && (cfg->topo_y == GB25_TOPO_BOUNDED || cfg->south_inactive);
+  g.wall_n = (cfg->ry == cfg->Ry - 1) && (cfg->topo_y == GB25_TOPO_BOUNDED);
   h->cfg.immersed = g.immersed;
   const size_t n2 = g.n2, n3 = n2 * g.PZ;
   const float* src2[13] = {grid->dx_cc, grid->dx_fc, grid->dx_cf, grid->dx_ff, grid->dy_cc, grid->dy_fc, grid->dy_cf, grid->dy_ff,
@@ -348,6 +351,7 @@ extern "C" int gb25_get_clock(const gb25_handle* h, double* time, long* iteratio
 extern "C" int gb25_synchronize(gb25_handle* h) {
   REQUIRE(h);
   CK(h, cudaStreamSynchronize(h->stream));
+  if (exchange_check_timeout(h)) { h->err = "halo exchange timed out waiting for a neighbour tile"; h->sticky = GB25_ERR_COMM; return GB25_ERR_COMM; }
   return check_async(h, "gb25_synchronize");
 }
 
@@ -521,12 +525,3 @@ extern "C" int gb25_get_stage_times(gb25_handle* h, const char** names, float* m
 }
 
 // ------------------------------------------------------------------ multi-GPU exchange (see gb25_exchange.cu)
-extern "C" int gb25_exchange_blob_size(void) { return 0; }
-extern "C" int gb25_exchange_export(gb25_handle* h, void*) {
-  if (!h) return GB25_ERR_INVALID;
-  h->err = "gb25_exchange_export: multi-GPU exchange is not built yet"; return GB25_ERR_COMM;
-}
-extern "C" int gb25_exchange_connect(gb25_handle* h, const void*, int) {
-  if (!h) return GB25_ERR_INVALID;
-  h->err = "gb25_exchange_connect: multi-GPU exchange is not built yet"; return GB25_ERR_COMM;
-}

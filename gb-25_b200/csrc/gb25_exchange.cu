@@ -1,0 +1,323 @@
+// gb25_exchange.cu — multi-GPU halo exchange, one process per GPU (row (e) of SURVEY.md §8).
+//
+// Replaces the XLA collective-permute traffic of Distributed(ReactantState(); partition=Partition(Rx,Ry,1))
+// (/root/reference/sharding/sharded_baroclinic_instability_simulation_run.jl:65-72).  Design for one NVSwitch box:
+//   * every rank exports the device allocations of its exchanged fields (u, v, T, S, eta, U, V, GU, GV) and a
+//     small flag array as CUDA IPC handles; neighbours map them, so a neighbour's halo cells are ordinary global
+//     addresses reached over NVLink;
+//   * PUSH model: the owner of the data writes the edge strips straight into the neighbours' halo cells with
+//     coalesced peer stores (no packing, no staging buffers, no NCCL call on the data path), then publishes a
+//     per-sender sequence number in the neighbour's flag array (system-scope fence + store);
+//   * the receiver's stream waits for the sequence numbers of exactly the tiles it receives from; the wait is a
+//     one-warp kernel spinning (bounded) on LOCAL memory — every rank owns its GPU, so no two spinning kernels
+//     ever share one;
+//   * two phases per fill, mirroring the single-tile order: y (south/north strips, tripolar fold with
+//     the x-mirrored partner, wall conditions on the boundary tiles), then x over the full parent extent so that
+//     corners are carried along.  No acknowledgements are needed: every site exchanges with the same neighbours
+//     in both directions, so a tile can only re-write a neighbour's halo after it has received something the
+//     neighbour sent after consuming the previous contents.
+#include <cstring>
+
+#include "gb25_internal.h"
+
+struct ExBlob {
+  cudaIpcMemHandle_t fld[EX_NF];
+  cudaIpcMemHandle_t flags;
+  int rank, Nx, Ny, Nz, Rx, Ry;
+};
+
+// --------------------------------------------------------------------------------- device side
+struct PushField { const float* src; float* dst; int lx, ly, lz; float sign; };
+struct PushBatch { PushField f[4]; int n; };
+
+// rows [srow, srow+nrows) of src -> rows [drow, ...) of dst; interior columns; planes [p0, p0+np)
+__global__ void k_push_rows(DevGrid g, PushBatch pb, int srow, int drow, int nrows, int p0, int np, int three_d) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x + g.Hx;
+  if (I >= g.Nx + g.Hx) return;
+  const int r = blockIdx.y % nrows, pl = blockIdx.y / nrows;
+  if (pl >= np) return;
+  const PushField pf = pb.f[blockIdx.z];
+  const size_t po = three_d ? (size_t)g.n2 * (p0 + pl) : 0;
+  pf.dst[po + (size_t)g.PX * (drow + r) + I] = pf.src[po + (size_t)g.PX * (srow + r) + I];
+}
+// columns [scol, scol+ncols) -> [dcol, ...); all rows; all planes
+__global__ void k_push_cols(DevGrid g, PushBatch pb, int scol, int dcol, int ncols, int three_d, int row0, int nrows_) {
+  const int cI = threadIdx.x;
+  const int J = row0 + blockIdx.x * blockDim.y + threadIdx.y;
+  if (cI >= ncols || J >= row0 + nrows_) return;
+  const PushField pf = pb.f[blockIdx.z];
+  const size_t po = (three_d ? (size_t)g.n2 * blockIdx.y : 0) + (size_t)g.PX * J;
+  pf.dst[po + dcol + cI] = pf.src[po + scol + cI];
+}
+// tripolar fold: my top rows -> the partner's north halo rows, x-mirrored, sign-flipped for vectors.
+// `second` selects the Face-x column whose partner lives one tile further (see the header comment of
+// fold_index_maps in grids.py / SURVEY A.5); quirk_pos: that element keeps |sign| (global wrap past Nx).
+__global__ void k_push_fold(DevGrid g, PushBatch pb, int three_d, int nrows, int second, int quirk_pos) {
+  const int is = blockIdx.x * blockDim.x + threadIdx.x + 1;   // source column (local, 1-based)
+  if (is > g.Nx) return;
+  const PushField pf = pb.f[blockIdx.z];
+  const int nk = three_d ? g.Nz + pf.lz : 1;
+  const int k = blockIdx.y + 1;
+  if (k > nk) return;
+  int id; float sg = pf.sign;
+  if (pf.lx == 0) { if (second) return; id = g.Nx - is + 1; }
+  else if (is == 1) { if (!second) return; id = 1; if (quirk_pos) sg = fabsf(sg); }
+  else { if (second) return; id = g.Nx + 2 - is; }
+  const size_t po = three_d ? (size_t)g.n2 * (k + g.Hz - 1) : 0;
+  for (int m = 1; m <= nrows; m++) {
+    const int js = pf.ly == 0 ? g.Ny - m : g.Ny - m + 1;
+    pf.dst[po + (size_t)g.PX * (g.Ny + m + g.Hy - 1) + id + g.Hx - 1] = sg * pf.src[po + (size_t)g.PX * (js + g.Hy - 1) + is + g.Hx - 1];
+  }
+}
+struct SignalSet { int* dst[EX_NSLOT]; int n; };
+__global__ void k_signal(SignalSet s, int val) {
+  __threadfence_system();
+  if ((int)threadIdx.x < s.n) *((volatile int*)s.dst[threadIdx.x]) = val;
+  __threadfence_system();
+}
+__global__ void k_wait(volatile int* flags, int mask, int val) {
+  const int t = threadIdx.x;
+  if (t < EX_NSLOT && ((mask >> t) & 1)) {
+    long spins = 0;
+    while (flags[t] < val) {
+      __nanosleep(200);
+      if (++spins > 20000000L) { flags[EX_NSLOT] = 1; break; }   // ~ several seconds: record a timeout, do not hang
+    }
+  }
+  __threadfence_system();
+}
+
+// --------------------------------------------------------------------------------- host side
+static int ex_field_id(Handle* h, const float* a) {
+  const DevFields& f = h->f;
+  const float* tab[EX_NF] = {f.u, f.v, f.T, f.S, f.eta, f.bu, f.bv, f.gU, f.gV};
+  for (int q = 0; q < EX_NF; q++) if (tab[q] == a) return q;
+  return -1;
+}
+static const ExSlot kOpposite[EX_NSLOT] = {SLOT_E, SLOT_W, SLOT_N, SLOT_S, SLOT_FOLD, SLOT_FOLD2};
+
+static PushBatch make_push(Handle* h, const HaloSpec* specs, int n, int slot, bool only_face_x = false) {
+  PushBatch pb; pb.n = 0;
+  for (int q = 0; q < n; q++) {
+    const int id = ex_field_id(h, specs[q].a);
+    if (id < 0) continue;
+    if (only_face_x && specs[q].lx == 0) continue;
+    pb.f[pb.n++] = PushField{specs[q].a, h->ex.to[slot].fld[id], specs[q].lx, specs[q].ly, specs[q].lz, specs[q].sign};
+  }
+  return pb;
+}
+static void signal_slots(Handle* h, int slot_mask) {
+  Exchange& X = h->ex;
+  SignalSet s; s.n = 0;
+  for (int sl = 0; sl < EX_NSLOT; sl++)
+    if (((slot_mask >> sl) & 1) && X.to[sl].rank >= 0 && X.to[sl].rank != X.rank) s.dst[s.n++] = X.to[sl].flags + kOpposite[sl];
+  if (s.n) { k_signal<<<1, 32, 0, h->stream>>>(s, X.seq); h->count_launch(); }
+}
+static void wait_slots(Handle* h, int slot_mask) {
+  Exchange& X = h->ex;
+  int m = 0;
+  for (int sl = 0; sl < EX_NSLOT; sl++)
+    if (((slot_mask >> sl) & 1) && X.to[sl].rank >= 0 && X.to[sl].rank != X.rank) m |= 1 << sl;
+  if (m) { k_wait<<<1, 32, 0, h->stream>>>(X.flags, m, X.seq); h->count_launch(); }
+}
+
+void launch_fill_halo_dist(Handle* h, const HaloSpec* specs, int n, bool three_d) {
+  Exchange& X = h->ex;
+  const DevGrid& g = h->g;
+  const gb25_config& c = h->cfg;
+  const bool top = c.ry == c.Ry - 1, bottom = c.ry == 0;
+  const bool fold = c.topo_y == GB25_TOPO_FOLD && top;
+  const int np = three_d ? g.PZ : 1;
+  // ---- wall conditions of the boundary tiles, then z halos of the interior columns (local)
+  launch_halo_south_north(h, specs, n, three_d, bottom ? 1 : 0, (top && c.topo_y == GB25_TOPO_BOUNDED) ? 1 : ((fold && c.Rx == 1) ? 2 : 0));
+  if (three_d) launch_halo_bottom_top(h, specs, n);
+  // ---- phase Y: strips to the north / south tiles (all planes), fold rows to the mirrored partner
+  int mask_y = 0;
+  dim3 b(128);
+  if (!top) {
+    PushBatch pb = make_push(h, specs, n, SLOT_N);
+    dim3 gr((g.Nx + 127) / 128, g.Hy * np, pb.n);
+    if (pb.n) { k_push_rows<<<gr, b, 0, h->stream>>>(g, pb, g.Ny, 0, g.Hy, 0, np, three_d); h->count_launch(); }   // rows Ny-Hy+1..Ny -> 1-Hy..0
+    mask_y |= 1 << SLOT_N;
+  }
+  if (!bottom) {
+    PushBatch pb = make_push(h, specs, n, SLOT_S);
+    dim3 gr((g.Nx + 127) / 128, g.Hy * np, pb.n);
+    if (pb.n) { k_push_rows<<<gr, b, 0, h->stream>>>(g, pb, g.Hy, g.Ny + g.Hy, g.Hy, 0, np, three_d); h->count_launch(); }  // rows 1..Hy -> Ny+1..Ny+Hy
+    mask_y |= 1 << SLOT_S;
+  }
+  if (fold && c.Rx > 1) {
+    int maxlz = 0;
+    for (int q = 0; q < n; q++) maxlz = max(maxlz, specs[q].lz);
+    const int nk = three_d ? g.Nz + maxlz : 1;
+    PushBatch pb = make_push(h, specs, n, SLOT_FOLD);
+    dim3 gr((g.Nx + 127) / 128, nk, pb.n);
+    if (pb.n) { k_push_fold<<<gr, b, 0, h->stream>>>(g, pb, three_d, g.Hy, 0, 0); h->count_launch(); }
+    PushBatch p2 = make_push(h, specs, n, SLOT_FOLD2, true);
+    dim3 g2(1, nk, p2.n);
+    if (p2.n) { k_push_fold<<<g2, b, 0, h->stream>>>(g, p2, three_d, g.Hy, 1, c.rx == 0 ? 1 : 0); h->count_launch(); }
+    mask_y |= (1 << SLOT_FOLD) | (1 << SLOT_FOLD2);
+  }
+  if (mask_y) { X.seq++; signal_slots(h, mask_y); wait_slots(h, mask_y); }
+  // ---- phase X: west / east strips over the full parent extent (carries the y and z halos into the corners)
+  if (c.Rx == 1) { launch_halo_periodic_x(h, specs, n, three_d); return; }
+  {
+    dim3 bc(g.Hx, 32), gc((g.PY + 31) / 32, np, 0);
+    PushBatch pe = make_push(h, specs, n, SLOT_E);   // my last Hx interior columns -> the east tile's west halo
+    gc.z = pe.n;
+    if (pe.n) { k_push_cols<<<gc, bc, 0, h->stream>>>(g, pe, g.Nx, 0, g.Hx, three_d, 0, g.PY); h->count_launch(); }
+    PushBatch pw = make_push(h, specs, n, SLOT_W);   // my first Hx interior columns -> the west tile's east halo
+    gc.z = pw.n;
+    if (pw.n) { k_push_cols<<<gc, bc, 0, h->stream>>>(g, pw, g.Hx, g.Nx + g.Hx, g.Hx, three_d, 0, g.PY); h->count_launch(); }
+    X.seq++;
+    const int mx = (1 << SLOT_W) | (1 << SLOT_E);
+    signal_slots(h, mx); wait_slots(h, mx);
+  }
+}
+
+// one-cell refresh of the barotropic halos between the substep kernels (no corners involved)
+void exchange_baro_eta(Handle* h) {   // after the eta kernel: the U,V kernel reads eta(i-1), eta(j-1)
+  Exchange& X = h->ex;
+  const DevGrid& g = h->g; const gb25_config& c = h->cfg;
+  HaloSpec s[1] = {{h->f.eta, 0, 0, 1, 1.f}};
+  int mask_out = 0, mask_in = 0;
+  if (c.Rx > 1) {
+    PushBatch pb = make_push(h, s, 1, SLOT_E);
+    dim3 bc(1, 128), gc((g.Ny + 127) / 128, 1, 1);
+    k_push_cols<<<gc, bc, 0, h->stream>>>(g, pb, g.Nx + g.Hx - 1, g.Hx - 1, 1, 0, g.Hy, g.Ny); h->count_launch();   // col Nx -> col 0
+    mask_out |= 1 << SLOT_E; mask_in |= 1 << SLOT_W;
+  }
+  if (c.ry < c.Ry - 1) {
+    PushBatch pb = make_push(h, s, 1, SLOT_N);
+    dim3 b(128), gr((g.Nx + 127) / 128, 1, 1);
+    k_push_rows<<<gr, b, 0, h->stream>>>(g, pb, g.Ny + g.Hy - 1, g.Hy - 1, 1, 0, 1, 0); h->count_launch();          // row Ny -> row 0
+    mask_out |= 1 << SLOT_N;
+  }
+  if (c.ry > 0) mask_in |= 1 << SLOT_S;
+  if (mask_out | mask_in) { X.seq++; signal_slots(h, mask_out); wait_slots(h, mask_in); }
+}
+void exchange_baro_uv(Handle* h) {    // after the U,V kernel: the eta kernel reads U(i+1), V(j+1)
+  Exchange& X = h->ex;
+  const DevGrid& g = h->g; const gb25_config& c = h->cfg;
+  HaloSpec su[1] = {{h->f.bu, 1, 0, 0, -1.f}}, sv[1] = {{h->f.bv, 0, 1, 0, -1.f}};
+  int mask_out = 0, mask_in = 0;
+  if (c.Rx > 1) {
+    PushBatch pb = make_push(h, su, 1, SLOT_W);
+    dim3 bc(1, 128), gc((g.Ny + 127) / 128, 1, 1);
+    k_push_cols<<<gc, bc, 0, h->stream>>>(g, pb, g.Hx, g.Nx + g.Hx, 1, 0, g.Hy, g.Ny); h->count_launch();           // col 1 -> col Nx+1
+    mask_out |= 1 << SLOT_W; mask_in |= 1 << SLOT_E;
+  }
+  if (c.ry > 0) {
+    PushBatch pb = make_push(h, sv, 1, SLOT_S);
+    dim3 b(128), gr((g.Nx + 127) / 128, 1, 1);
+    k_push_rows<<<gr, b, 0, h->stream>>>(g, pb, g.Hy, g.Ny + g.Hy, 1, 0, 1, 0); h->count_launch();                   // row 1 -> row Ny+1
+    mask_out |= 1 << SLOT_S;
+  }
+  if (c.ry < c.Ry - 1) mask_in |= 1 << SLOT_N;
+  if (c.topo_y == GB25_TOPO_FOLD && c.ry == c.Ry - 1 && c.Rx > 1) {
+    PushBatch pb = make_push(h, sv, 1, SLOT_FOLD);
+    dim3 b(128), gr((g.Nx + 127) / 128, 1, 1);
+    k_push_fold<<<gr, b, 0, h->stream>>>(g, pb, 0, 1, 0, 0); h->count_launch();                                     // V(i, Ny+1) = -V(Nx-i+1, Ny)
+    mask_out |= 1 << SLOT_FOLD; mask_in |= 1 << SLOT_FOLD;
+  }
+  if (mask_out | mask_in) { X.seq++; signal_slots(h, mask_out); wait_slots(h, mask_in); }
+}
+
+// --------------------------------------------------------------------------------- C ABI
+extern "C" int gb25_exchange_blob_size(void) { return (int)sizeof(ExBlob); }
+
+extern "C" int gb25_exchange_export(gb25_handle* h, void* blob) {
+  if (!h || !blob) return GB25_ERR_INVALID;
+  cudaSetDevice(h->device);
+  ExBlob b; memset(&b, 0, sizeof b);
+  Exchange& X = h->ex;
+  if (!X.flags) {
+    // a dedicated 2 MiB allocation so that the IPC handle maps exactly this buffer
+    if (cudaMalloc(&X.flags, 2 << 20) != cudaSuccess) { h->err = "gb25_exchange_export: cudaMalloc flags"; return GB25_ERR_ALLOC; }
+    cudaMemset(X.flags, 0, 2 << 20);
+  }
+  const DevFields& f = h->f;
+  float* tab[EX_NF] = {f.u, f.v, f.T, f.S, f.eta, f.bu, f.bv, f.gU, f.gV};
+  for (int q = 0; q < EX_NF; q++) {
+    cudaError_t e = cudaIpcGetMemHandle(&b.fld[q], tab[q]);
+    if (e != cudaSuccess) { h->err = std::string("gb25_exchange_export: cudaIpcGetMemHandle: ") + cudaGetErrorString(e); return GB25_ERR_COMM; }
+  }
+  cudaError_t e = cudaIpcGetMemHandle(&b.flags, X.flags);
+  if (e != cudaSuccess) { h->err = std::string("gb25_exchange_export: cudaIpcGetMemHandle(flags): ") + cudaGetErrorString(e); return GB25_ERR_COMM; }
+  const gb25_config& c = h->cfg;
+  b.rank = c.rx + c.Rx * c.ry; b.Nx = c.Nx; b.Ny = c.Ny; b.Nz = c.Nz; b.Rx = c.Rx; b.Ry = c.Ry;
+  memcpy(blob, &b, sizeof b);
+  return GB25_OK;
+}
+
+extern "C" int gb25_exchange_connect(gb25_handle* h, const void* blobs, int nranks) {
+  if (!h || !blobs) return GB25_ERR_INVALID;
+  cudaSetDevice(h->device);
+  const gb25_config& c = h->cfg;
+  Exchange& X = h->ex;
+  if (nranks != c.Rx * c.Ry) { h->err = "gb25_exchange_connect: nranks != Rx*Ry"; return GB25_ERR_INVALID; }
+  if (!X.flags) { h->err = "gb25_exchange_connect: call gb25_exchange_export first"; return GB25_ERR_INVALID; }
+  if (c.fold_variant == 1 && c.Rx > 1 && c.topo_y == GB25_TOPO_FOLD) { h->err = "gb25_exchange_connect: fold_variant 1 is only implemented for Rx == 1"; return GB25_ERR_INVALID; }
+  const ExBlob* B = (const ExBlob*)blobs;
+  X.nranks = nranks; X.rank = c.rx + c.Rx * c.ry;
+  for (int r = 0; r < nranks; r++)
+    if (B[r].rank != r || B[r].Nx != c.Nx || B[r].Ny != c.Ny || B[r].Nz != c.Nz || B[r].Rx != c.Rx || B[r].Ry != c.Ry) {
+      h->err = "gb25_exchange_connect: blobs must be ordered by rank and describe equal tiles"; return GB25_ERR_INVALID;
+    }
+  auto rk = [&](int rx, int ry) { return ((rx % c.Rx) + c.Rx) % c.Rx + c.Rx * ry; };
+  int want[EX_NSLOT];
+  for (int s = 0; s < EX_NSLOT; s++) want[s] = -1;
+  if (c.Rx > 1) { want[SLOT_W] = rk(c.rx - 1, c.ry); want[SLOT_E] = rk(c.rx + 1, c.ry); }
+  if (c.ry > 0) want[SLOT_S] = rk(c.rx, c.ry - 1);
+  if (c.ry < c.Ry - 1) want[SLOT_N] = rk(c.rx, c.ry + 1);
+  if (c.topo_y == GB25_TOPO_FOLD && c.ry == c.Ry - 1 && c.Rx > 1) {
+    want[SLOT_FOLD] = rk(c.Rx - 1 - c.rx, c.ry);
+    want[SLOT_FOLD2] = rk(c.Rx - c.rx, c.ry);
+  }
+  // map every distinct peer once
+  std::vector<ExPeer> mapped(nranks);
+  std::vector<char> have(nranks, 0);
+  const DevFields& f = h->f;
+  float* mine[EX_NF] = {f.u, f.v, f.T, f.S, f.eta, f.bu, f.bv, f.gU, f.gV};
+  for (int s = 0; s < EX_NSLOT; s++) {
+    const int r = want[s];
+    X.to[s].rank = r;
+    if (r < 0) continue;
+    if (!have[r]) {
+      ExPeer p; p.rank = r;
+      if (r == X.rank) {
+        for (int q = 0; q < EX_NF; q++) p.fld[q] = mine[q];
+        p.flags = X.flags;
+      } else {
+        for (int q = 0; q < EX_NF; q++) {
+          void* ptr = nullptr;
+          cudaError_t e = cudaIpcOpenMemHandle(&ptr, B[r].fld[q], cudaIpcMemLazyEnablePeerAccess);
+          if (e != cudaSuccess) { h->err = std::string("gb25_exchange_connect: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); return GB25_ERR_COMM; }
+          X.opened.push_back(ptr); p.fld[q] = (float*)ptr;
+        }
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, B[r].flags, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { h->err = std::string("gb25_exchange_connect: cudaIpcOpenMemHandle(flags): ") + cudaGetErrorString(e); return GB25_ERR_COMM; }
+        X.opened.push_back(ptr); p.flags = (int*)ptr;
+      }
+      mapped[r] = p; have[r] = 1;
+    }
+    X.to[s] = mapped[r];
+  }
+  X.seq = 0;
+  X.on = true;
+  return GB25_OK;
+}
+
+int exchange_check_timeout(Handle* h) {
+  if (!h->ex.on) return 0;
+  int flag = 0;
+  cudaMemcpy(&flag, h->ex.flags + EX_NSLOT, sizeof(int), cudaMemcpyDeviceToHost);
+  return flag;
+}
+void exchange_close(Handle* h) {
+  for (void* p : h->ex.opened) cudaIpcCloseMemHandle(p);
+  h->ex.opened.clear();
+  if (h->ex.flags) { cudaFree(h->ex.flags); h->ex.flags = nullptr; }
+  h->ex.on = false;
+}

@@ -10,6 +10,20 @@
 
 struct HaloSpec { float* a; int lx, ly, lz; float sign; };
 
+// ---- multi-GPU halo exchange over peer-mapped (CUDA IPC) memory, one process per GPU (gb25_exchange.cu)
+enum ExField { EX_U = 0, EX_V, EX_T, EX_S, EX_ETA, EX_BU, EX_BV, EX_GU, EX_GV, EX_NF };
+enum ExSlot { SLOT_W = 0, SLOT_E, SLOT_S, SLOT_N, SLOT_FOLD, SLOT_FOLD2, EX_NSLOT };
+struct ExPeer { float* fld[EX_NF]; int* flags; int rank; };
+struct Exchange {
+  bool on = false;
+  int nranks = 1, rank = 0;
+  int* flags = nullptr;          // local inbox: EX_NSLOT sequence numbers written by the neighbours + 1 error word
+  ExPeer to[EX_NSLOT];           // the tile lying in that direction (destination of my pushes); rank < 0: none
+  int from_mask_y = 0, from_mask_x = 0, from_mask_fold = 0;   // slots I receive on in each phase
+  int seq = 0;
+  std::vector<void*> opened;     // pointers returned by cudaIpcOpenMemHandle
+};
+
 struct StageTimer {
   const char* name;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
@@ -35,6 +49,7 @@ struct gb25_handle {
   double time = 0.0;
   long iteration = 0;
   float last_dt = 0.f;
+  Exchange ex;
   // errors
   std::string err;
   int sticky = 0;
@@ -60,6 +75,14 @@ typedef gb25_handle Handle;
 
 // stage launchers (gb25_kernels.cu)
 void launch_fill_halo(Handle* h, const HaloSpec* specs, int n, bool three_d);
+void launch_halo_south_north(Handle* h, const HaloSpec* specs, int n, bool three_d, int mode_s, int mode_n);
+void launch_halo_bottom_top(Handle* h, const HaloSpec* specs, int n);
+void launch_halo_periodic_x(Handle* h, const HaloSpec* specs, int n, bool three_d);
+void launch_fill_halo_dist(Handle* h, const HaloSpec* specs, int n, bool three_d);   // gb25_exchange.cu
+void exchange_baro_eta(Handle* h);
+void exchange_baro_uv(Handle* h);
+int exchange_check_timeout(Handle* h);
+void exchange_close(Handle* h);
 void launch_mask(Handle* h, bool uv_only);
 void launch_compute_w(Handle* h);
 void launch_compute_p(Handle* h);

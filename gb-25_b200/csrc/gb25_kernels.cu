@@ -11,7 +11,8 @@ struct HaloField { float* a; int lx, ly, lz; float sign; };
 struct HaloBatch { HaloField f[4]; int n; };
 
 // south/north of 3-D or 2-D fields: threads over (i, k, field); loop over the halo depth
-__global__ void k_halo_south_north(DevGrid g, HaloBatch hb, int three_d) {
+// mode_s: 0 = nothing (a neighbour tile fills it), 1 = local wall BC.  mode_n: 0 = nothing, 1 = wall BC, 2 = local fold.
+__global__ void k_halo_south_north(DevGrid g, HaloBatch hb, int three_d, int mode_s, int mode_n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int fidx = blockIdx.z;
   if (i > g.Nx) return;
@@ -23,12 +24,14 @@ __global__ void k_halo_south_north(DevGrid g, HaloBatch hb, int three_d) {
   const int PX = g.PX, Hx = g.Hx, Hy = g.Hy, Ny = g.Ny, Nx = g.Nx;
   const int I = i + Hx - 1;
 #define A2(ii, jj) a[(ii) + PX * ((jj) + Hy - 1)]
-  if (hf.ly == 0) { for (int m = 1; m <= Hy; m++) A2(I, 1 - m) = A2(I, m); }
-  else A2(I, 1) = 0.f;
-  if (g.topo_y == 0) {
+  if (mode_s == 1) {
+    if (hf.ly == 0) { for (int m = 1; m <= Hy; m++) A2(I, 1 - m) = A2(I, m); }
+    else A2(I, 1) = 0.f;
+  }
+  if (mode_n == 1) {
     if (hf.ly == 0) { for (int m = 1; m <= Hy; m++) A2(I, Ny + m) = A2(I, Ny + 1 - m); }
     else A2(I, Ny + 1) = 0.f;
-  } else {
+  } else if (mode_n == 2) {
     int ip; float sg = hf.sign;
     if (hf.lx == 0) ip = Nx - i + 1;
     else { ip = Nx - i + 2; if (ip > Nx) { ip -= Nx; sg = fabsf(sg); } }
@@ -62,7 +65,7 @@ __global__ void k_halo_bottom_top(DevGrid g, HaloBatch hb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
   const int j = blockIdx.y + 1;
   const HaloField hf = hb.f[blockIdx.z];
-  const int jt = g.Ny + ((hf.ly && g.topo_y == 0) ? 1 : 0);
+  const int jt = g.Ny + ((hf.ly && g.wall_n) ? 1 : 0);
   if (i > g.Nx || j > jt) return;
   float* a = hf.a + id2(g, i, j);
   const size_t n2 = g.n2; const int Hz = g.Hz, Nz = g.Nz;
@@ -84,24 +87,40 @@ __global__ void k_halo_periodic_x(DevGrid g, HaloBatch hb, int three_d) {
   else a[g.Nx + t] = a[t];
 }
 
-void launch_fill_halo(Handle* h, const HaloSpec* specs, int n, bool three_d) {
+static HaloBatch make_batch(const HaloSpec* specs, int n, int* maxlz) {
+  HaloBatch hb; hb.n = n; *maxlz = 0;
+  for (int q = 0; q < n; q++) { hb.f[q] = HaloField{specs[q].a, specs[q].lx, specs[q].ly, specs[q].lz, specs[q].sign}; *maxlz = max(*maxlz, specs[q].lz); }
+  return hb;
+}
+void launch_halo_south_north(Handle* h, const HaloSpec* specs, int n, bool three_d, int mode_s, int mode_n) {
   const DevGrid& g = h->g;
-  HaloBatch hb; hb.n = n;
-  int maxlz = 0;
-  for (int q = 0; q < n; q++) { hb.f[q] = HaloField{specs[q].a, specs[q].lx, specs[q].ly, specs[q].lz, specs[q].sign}; maxlz = max(maxlz, specs[q].lz); }
+  int maxlz; HaloBatch hb = make_batch(specs, n, &maxlz);
   const int nk = three_d ? g.Nz + maxlz : 1;
   dim3 b1(128), g1((g.Nx + 127) / 128, nk, n);
-  k_halo_south_north<<<g1, b1, 0, h->stream>>>(g, hb, three_d); h->count_launch();
-  if (g.topo_y == 1 && g.fold_variant == 1) {
+  if (mode_s || mode_n) { k_halo_south_north<<<g1, b1, 0, h->stream>>>(g, hb, three_d, mode_s, mode_n); h->count_launch(); }
+  if (mode_n == 2 && g.fold_variant == 1) {
     dim3 gf((g.Nx / 2 + 127) / 128, nk, n);
     k_halo_fold_row<<<gf, b1, 0, h->stream>>>(g, hb, three_d); h->count_launch();
   }
-  if (three_d) {
-    dim3 g2((g.Nx + 127) / 128, g.Ny + 1, n);
-    k_halo_bottom_top<<<g2, b1, 0, h->stream>>>(g, hb); h->count_launch();
-  }
+}
+void launch_halo_bottom_top(Handle* h, const HaloSpec* specs, int n) {
+  const DevGrid& g = h->g;
+  int maxlz; HaloBatch hb = make_batch(specs, n, &maxlz);
+  dim3 b1(128), g2((g.Nx + 127) / 128, g.Ny + 1, n);
+  k_halo_bottom_top<<<g2, b1, 0, h->stream>>>(g, hb); h->count_launch();
+}
+void launch_halo_periodic_x(Handle* h, const HaloSpec* specs, int n, bool three_d) {
+  const DevGrid& g = h->g;
+  int maxlz; HaloBatch hb = make_batch(specs, n, &maxlz);
   dim3 b3(2 * g.Hx, 16), g3((g.PY + 15) / 16, three_d ? g.PZ : 1, n);
   k_halo_periodic_x<<<g3, b3, 0, h->stream>>>(g, hb, three_d); h->count_launch();
+}
+void launch_fill_halo(Handle* h, const HaloSpec* specs, int n, bool three_d) {
+  if (h->ex.on) { launch_fill_halo_dist(h, specs, n, three_d); return; }
+  const DevGrid& g = h->g;
+  launch_halo_south_north(h, specs, n, three_d, 1, g.topo_y == 0 ? 1 : 2);
+  if (three_d) launch_halo_bottom_top(h, specs, n);
+  launch_halo_periodic_x(h, specs, n, three_d);
 }
 
 // =====================================================================================
@@ -278,16 +297,19 @@ void launch_ab2_columns(Handle* h, float dt, float chi) {
 // =====================================================================================
 // Split-explicit substeps (row A10): forward-backward, topology-aware differences
 // =====================================================================================
-__global__ void k_baro_eta(DevGrid g, float* __restrict__ eta, const float* __restrict__ U, const float* __restrict__ V, float dtau) {
+// Edge handling: a tile that spans the whole direction applies the topology itself (periodic wrap, wall, fold);
+// on a partitioned grid the one-cell halos of eta / U / V are refreshed by the neighbours after every kernel.
+//   bflags bit 0: wrap in x locally (Rx == 1); bit 1: south wall; bit 2: north wall; bit 3: local north fold
+__global__ void k_baro_eta(DevGrid g, float* __restrict__ eta, const float* __restrict__ U, const float* __restrict__ V, float dtau, int bflags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
   if (i > g.Nx) return;
   const int q2 = id2(g, i, j), PX = g.PX;
-  const int qe = (i == g.Nx) ? id2(g, 1, j) : q2 + 1;
+  const int qe = (i == g.Nx && (bflags & 1)) ? id2(g, 1, j) : q2 + 1;
   const float dU = g.dyfc[qe] * U[qe] - g.dyfc[q2] * U[q2];
   float dV;
-  if (j == 1) dV = g.dxcf[q2 + PX] * V[q2 + PX];
-  else if (j == g.Ny) {
-    if (g.topo_y == 0) dV = -(g.dxcf[q2] * V[q2]);
+  if (j == 1 && (bflags & 2)) dV = g.dxcf[q2 + PX] * V[q2 + PX];
+  else if (j == g.Ny && (bflags & 12)) {
+    if (bflags & 4) dV = -(g.dxcf[q2] * V[q2]);
     else {  // folded row Ny+1: V[i,Ny+1] = -V[Nx-i+1,Ny]
       const float vn = -V[id2(g, g.Nx - i + 1, g.Ny)];
       dV = g.dxcf[q2 + PX] * vn - g.dxcf[q2] * V[q2];
@@ -295,14 +317,14 @@ __global__ void k_baro_eta(DevGrid g, float* __restrict__ eta, const float* __re
   } else dV = g.dxcf[q2 + PX] * V[q2 + PX] - g.dxcf[q2] * V[q2];
   eta[q2] -= dtau * (dU + dV) / g.azcc[q2];
 }
-__global__ void k_baro_uv(DevGrid g, DevFields f, float dtau, float wgt) {
+__global__ void k_baro_uv(DevGrid g, DevFields f, float dtau, float wgt, int bflags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
   if (i > g.Nx) return;
   const int q2 = id2(g, i, j);
-  const int qw = (i == 1) ? id2(g, g.Nx, j) : q2 - 1;
+  const int qw = (i == 1 && (bflags & 1)) ? id2(g, g.Nx, j) : q2 - 1;
   const float e0 = f.eta[q2];
   const float dxe = (e0 - f.eta[qw]) / g.dxfc[q2];
-  const float dye = (j == 1) ? 0.f : (e0 - f.eta[q2 - g.PX]) / g.dycf[q2];
+  const float dye = (j == 1 && (bflags & 2)) ? 0.f : (e0 - f.eta[q2 - g.PX]) / g.dycf[q2];
   const float Un = f.bu[q2] + dtau * (-g.g * g.Hfc[q2] * dxe + f.gU[q2]);
   const float Vn = f.bv[q2] + dtau * (-g.g * g.Hcf[q2] * dye + f.gV[q2]);
   f.bu[q2] = Un; f.bv[q2] = Vn;
@@ -324,9 +346,14 @@ void launch_barotropic(Handle* h, float dt) {
   cudaMemsetAsync(h->f.fv, 0, b2, h->stream);
   const float dtau = h->cfg.dtau_frac * dt;
   dim3 b(128), gr((g.Nx + 127) / 128, g.Ny);
+  const gb25_config& c = h->cfg;
+  const int bflags = (c.Rx == 1 ? 1 : 0) | (c.ry == 0 ? 2 : 0) | ((c.ry == c.Ry - 1 && c.topo_y == GB25_TOPO_BOUNDED) ? 4 : 0) |
+                     ((c.ry == c.Ry - 1 && c.topo_y == GB25_TOPO_FOLD && c.Rx == 1) ? 8 : 0);
   for (int m = 0; m < h->cfg.nsubsteps; m++) {
-    k_baro_eta<<<gr, b, 0, h->stream>>>(g, h->f.eta, h->f.bu, h->f.bv, dtau); h->count_launch();
-    k_baro_uv<<<gr, b, 0, h->stream>>>(g, h->f, dtau, h->weights[m]); h->count_launch();
+    k_baro_eta<<<gr, b, 0, h->stream>>>(g, h->f.eta, h->f.bu, h->f.bv, dtau, bflags); h->count_launch();
+    if (h->ex.on) exchange_baro_eta(h);
+    k_baro_uv<<<gr, b, 0, h->stream>>>(g, h->f, dtau, h->weights[m], bflags); h->count_launch();
+    if (h->ex.on) exchange_baro_uv(h);
   }
   k_baro_finish<<<gr, b, 0, h->stream>>>(g, h->f); h->count_launch();
 }

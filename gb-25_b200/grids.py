@@ -67,6 +67,8 @@ class Grid:
     lam_cc: np.ndarray       # physical longitude / latitude of (C,C) nodes, degrees, (PY, PX)
     phi_cc: np.ndarray
     kind: str = "latlon"
+    # tiles of a partitioned grid: does THIS tile own the north wall (Bounded y)?  None = whole domain
+    wall_n: bool | None = None
 
     @property
     def PX(self): return self.Nx + 2 * self.Hx
@@ -84,9 +86,13 @@ class Grid:
         """Oceananigans parent shape (x, y, z) for a field at ``loc`` = (lx, ly, lz), 1 = Face.
         Bounded-Face has N+1 points; Periodic / RightConnected Face has N."""
         lx, ly, lz = loc
-        ny = self.Ny + (1 if (ly == 1 and self.topo_y == TOPO_BOUNDED) else 0)
+        ny = self.Ny + (1 if (ly == 1 and self.owns_north_wall) else 0)
         nz = self.Nz + (1 if lz == 1 else 0)
         return (self.Nx + 2 * self.Hx, ny + 2 * self.Hy, nz + 2 * self.Hz)
+
+    @property
+    def owns_north_wall(self):
+        return (self.topo_y == TOPO_BOUNDED) if self.wall_n is None else bool(self.wall_n)
 
 
 def _vertical(Nz, Hz, z_faces):

@@ -47,7 +47,7 @@ class Clock:
 
 def _interior_slices(grid, loc):
     lx, ly, lz, three_d = loc
-    ny = grid.Ny + (1 if (ly and grid.topo_y == _grids.TOPO_BOUNDED) else 0)
+    ny = grid.Ny + (1 if (ly and grid.owns_north_wall) else 0)
     nz = grid.Nz + (1 if lz else 0)
     sx = slice(grid.Hx, grid.Hx + grid.Nx)
     sy = slice(grid.Hy, grid.Hy + ny)
