@@ -141,7 +141,7 @@ static int build_immersed_products(Handle* h, const gb25_grid* grid) {
     if (I < 0 || I >= PX || J < 0 || J >= PY) return GB25_BIG;  // beyond the stored halo: treat as solid
     return a[I + PX * J];
   };
-  std::vector<short> fx3(n2), fx2(n2), fy3(n2), fy2(n2), cx3(n2), cx2(n2), cy3(n2), cy2(n2), knear(n2);
+  std::vector<short> fx3(n2), fx2(n2), fy3(n2), fy2(n2), cx3(n2), cx2(n2), cy3(n2), cy2(n2), knear(n2), ksolid(n2);
   for (int J = 0; J < PY; J++)
     for (int I = 0; I < PX; I++) {
       const int q = I + PX * J;
@@ -159,6 +159,12 @@ static int build_immersed_products(Handle* h, const gb25_grid* grid) {
       m = 0;
       for (int dj = -4; dj <= 4; dj++) for (int di = -4; di <= 4; di++) m = std::max(m, at(kbe, I + di, J + dj));
       knear[q] = (short)m;
+      int mn = GB25_BIG;
+      for (int dj = -4; dj <= 4; dj++) for (int di = -4; di <= 4; di++) {
+        const int II = I + di, JJ = J + dj;
+        mn = std::min(mn, (II < 0 || II >= PX || JJ < 0 || JJ >= PY) ? 0 : (int)kb[II + PX * JJ]);
+      }
+      ksolid[q] = (short)mn;
     }
   int rc;
   if ((rc = upload(h, kb.data(), n2, &h->g.kb))) return rc;
@@ -171,6 +177,7 @@ static int build_immersed_products(Handle* h, const gb25_grid* grid) {
   if ((rc = upload(h, cy3.data(), n2, &h->g.cy3))) return rc;
   if ((rc = upload(h, cy2.data(), n2, &h->g.cy2))) return rc;
   if ((rc = upload(h, knear.data(), n2, &h->g.knear))) return rc;
+  if ((rc = upload(h, ksolid.data(), n2, &h->g.ksolid))) return rc;
   if ((rc = upload(h, Hfc.data(), n2, &h->g.Hfc))) return rc;
   if ((rc = upload(h, Hcf.data(), n2, &h->g.Hcf))) return rc;
   return GB25_OK;

@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(128) k_tracer_tendency_v2(DevGrid g, const Dev
   // ---- hoisted 2-D data
   float dyf[NC + 1], dxs[NC], dxn[NC], az[NC];
   int kgen = 0;   // levels k <= kgen (bathymetry / walls somewhere in the stencil) take the generic path
+  int kzero = GB25_BIG;   // levels k <= kzero: the whole stencil is solid rock, every flux is masked, G = 0
   int kbc[NC];
 #pragma unroll
   for (int e = 0; e <= NC; e++) dyf[e] = g.dyfc[q2 + e];
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(128) k_tracer_tendency_v2(DevGrid g, const Dev
     dxs[c] = g.dxcf[q2 + c]; dxn[c] = g.dxcf[q2 + PX + c]; az[c] = g.azcc[q2 + c];
     kbc[c] = g.kb[q2 + c];
     kgen = max(kgen, (int)g.knear[q2 + c] + 1);
+    kzero = min(kzero, (int)g.ksolid[q2 + c] - 3);
   }
   // ---- vertical register window: WT[c][m] = T(i0+c, j, k-3+m)
   size_t q3 = q2 + (size_t)n2 * g.Hz;  // level k = 1
@@ -86,7 +88,10 @@ __global__ void __launch_bounds__(128) k_tracer_tendency_v2(DevGrid g, const Dev
   for (int c = 0; c < NC; c++) FzT[c] = 0.f;
   for (int k = 1; k <= Nz; k++, q3 += n2) {
     float oT[NC];
-    if (k <= kgen) {   // always taken at k = 1, so the carried flux is valid from the first fast level on
+    if (k <= kzero) {
+#pragma unroll
+      for (int c = 0; c < NC; c++) { oT[c] = 0.f; FzT[c] = 0.f; }
+    } else if (k <= kgen) {   // always taken at k = 1 (or kzero + 1), so the carried flux is valid on the fast levels
       for (int c = 0; c < NC; c++) {
         float ft;
         const float o = tracer_cell_generic1(gp, u, v, w, T, i0 + c, j, k, &ft);
@@ -255,9 +260,10 @@ __global__ void __launch_bounds__(128) k_gu_v2(DevGrid g, const DevGrid* __restr
   const float eps = g.eps;
   // ---- hoisted 2-D data
   float m1[NC], rV0[NC], fbar[NC], mv[2][NC + 1], azw[NC + 3];
-  int kbc[NC], kgen = 0;
+  int kbc[NC], kgen = 0, kzero = GB25_BIG;
 #pragma unroll
   for (int c = 0; c < NC; c++) {
+    kzero = min(kzero, g.cond_diff ? (int)g.ksolid[q2 + c] - 3 : 0);
     m1[c] = g.dxfc[q2 + c];
     rV0[c] = g.azfc[q2 + c];
     fbar[c] = (g.fff[q2 + c] + g.fff[q2 + c + PX]) * 0.5f;
@@ -279,7 +285,9 @@ __global__ void __launch_bounds__(128) k_gu_v2(DevGrid g, const DevGrid* __restr
   float Wb[NC] = {0.f, 0.f};   // carried vertical flux through the bottom face (set by the generic path at k = 1)
   for (int k = 1; k <= Nz; k++, q3 += n2) {
     float out[NC];
-    if (k <= kgen) {
+    if (k <= kzero) {   // solid rock all around: u = v = 0, every flux masked, pressure difference conditional => G = 0
+      out[0] = out[1] = 0.f; Wb[0] = Wb[1] = 0.f;
+    } else if (k <= kgen) {
       for (int c = 0; c < NC; c++) {
         float wt;
         const float o = momentum_G_call<0>(gp, u, v, w, p, i0 + c, j, k, &wt);
@@ -397,9 +405,10 @@ __global__ void __launch_bounds__(128) k_gv_v2(DevGrid g, const DevGrid* __restr
   const float eps = g.eps;
   // ---- hoisted 2-D data
   float m1[NC], rV0[NC], fbar[NC], mu[2][NC + 1], azw[4][NC];
-  int kbc[NC], kgen = 0;
+  int kbc[NC], kgen = 0, kzero = GB25_BIG;
 #pragma unroll
   for (int c = 0; c < NC; c++) {
+    kzero = min(kzero, g.cond_diff ? (int)g.ksolid[q2 + c] - 3 : 0);
     m1[c] = g.dycf[q2 + c];
     rV0[c] = g.azcf[q2 + c];
     fbar[c] = (g.fff[q2 + c] + g.fff[q2 + c + 1]) * 0.5f;
@@ -421,7 +430,9 @@ __global__ void __launch_bounds__(128) k_gv_v2(DevGrid g, const DevGrid* __restr
   float Wb[NC] = {0.f, 0.f};
   for (int k = 1; k <= Nz; k++, q3 += n2) {
     float out[NC];
-    if (k <= kgen) {
+    if (k <= kzero) {
+      out[0] = out[1] = 0.f; Wb[0] = Wb[1] = 0.f;
+    } else if (k <= kgen) {
       for (int c = 0; c < NC; c++) {
         float wt;
         const float o = momentum_G_call<1>(gp, v, u, w, p, i0 + c, j, k, &wt);
