@@ -190,6 +190,7 @@ extern "C" int gb25_destroy(gb25_handle* h) {
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->graph) cudaGraphDestroy(h->graph);
   exchange_close(h);
+  tma_free(h);
   for (void* p : h->allocs) cudaFree(p);
   if (h->stage_dev) cudaFree(h->stage_dev);
   for (auto& s : h->timers) for (auto& e : s.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -294,6 +295,8 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
   {
     const char* e = getenv("GB25_FUSED");
     h->use_fused = !(e && e[0] == '0');
+    const char* t = getenv("GB25_TMA");
+    h->use_tma = !(t && t[0] == '0');
   }
   DevFields& f = h->f;
   f.u = h->field_ptr[GB25_U]; f.v = h->field_ptr[GB25_V]; f.w = h->field_ptr[GB25_W];

@@ -68,6 +68,8 @@ struct gb25_handle {
   float graph_dt = 0.f;
   long graph_launches = 0;
   bool use_fused = true;
+  bool use_tma = true;
+  void* tma = nullptr;   // TMA tensor maps (gb25_tend_tma.cu)
 
   inline void count_launch() { launches++; }
 };
@@ -91,7 +93,10 @@ void launch_tracer_tendency_v1(Handle* h);
 void launch_tracer_tendency_v2(Handle* h);   // gb25_tend_v2.cu
 void launch_momentum_tendency_v1(Handle* h);
 void launch_momentum_tendency_v2(Handle* h);  // gb25_tend_v2.cu
-void launch_aux_columns(Handle* h);           // gb25_tend_v2.cu: w + zeta + flux divergences in one column pass
+void launch_aux_columns(Handle* h);
+void launch_momentum_tendency_tma(Handle* h);   // gb25_tend_tma.cu
+bool tma_available(Handle* h);
+void tma_free(Handle* h);           // gb25_tend_v2.cu: w + zeta + flux divergences in one column pass
 void launch_momentum_tendency(Handle* h);
 void launch_ab2_columns(Handle* h, float dt, float chi);
 void launch_barotropic(Handle* h, float dt);

@@ -1,0 +1,409 @@
+// gb25_tend_tma.cu — third-generation momentum tendency kernels: TMA-staged halo'd tiles, k-marching.
+//
+// ncu of the second generation (profiles/): half the instructions of the first, but only ~42 % issue-slot
+// utilisation at 16-20 % occupancy — every level starts with ~40 dependent global loads per thread and there are
+// too few warps to hide them.  Here the loads leave the instruction stream altogether:
+//   * a CTA owns a 32 x 8 tile of columns and marches k = 1..Nz, one cell per thread;
+//   * for every level one elected thread issues 3-D TMA box loads (cp.async.bulk.tensor) of the halo'd tiles of
+//     u, v, zeta, dxU, dyV, w(k+1) and p into a 3-stage shared-memory ring, two levels ahead, completion tracked by
+//     one mbarrier per stage (expect_tx / complete_tx);
+//   * the arithmetic reads its stencils from shared memory with immediate offsets (no address arithmetic, no
+//     dependence on L1 hit rates), the vertical stencil of the own velocity lives in a register window, the
+//     vertical momentum flux is carried from face to face;
+//   * cells whose stencil touches bathymetry or a wall use the generic per-cell function (global memory), and
+//     cells buried in rock are written as zero, exactly as in gb25_tend_v2.cu.
+// The arithmetic (expression by expression) is that of k_gu_v2 / k_gv_v2, so the results are bit-identical.
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
+
+#include "gb25_internal.h"
+#include "gb25_tend_generic.cuh"
+
+#define TMA_TX 32
+#define TMA_TY 8
+#define TMA_NST 3
+
+// ----------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+template <int DIR>
+static __device__ __noinline__ float momentum_G_call3(const DevGrid* __restrict__ gp, const float* __restrict__ own,
+                                                      const float* __restrict__ oth, const float* __restrict__ w,
+                                                      const float* __restrict__ p, int i, int j, int k, float* wtop) {
+  return momentum_G<DIR>(*gp, own, oth, w, p, i, j, k, wtop);
+}
+__device__ __forceinline__ float weno_sel_B3(float q0, float q1, float q2, float q3, float q4, float q5, int B, bool left, float eps) {
+  if (B == 3) {
+    const float v0 = left ? q0 : q5, v1 = left ? q1 : q4, v2 = left ? q2 : q3, v3 = left ? q3 : q2, v4 = left ? q4 : q1;
+    return weno5(v0, v1, v2, v3, v4, eps);
+  }
+  if (B == 2) return left ? weno3(q1, q2, q3, eps) : weno3(q4, q3, q2, eps);
+  return left ? q2 : q3;
+}
+__device__ __forceinline__ float weno5_fs_sel3(const float (&q)[6], const float (&s)[6], bool left, float eps) {
+  return left ? weno5_fs(q[0], q[1], q[2], q[3], q[4], s[0], s[1], s[2], s[3], s[4], eps)
+              : weno5_fs(q[5], q[4], q[3], q[2], q[1], s[5], s[4], s[3], s[2], s[1], eps);
+}
+
+struct TmaMaps7 { CUtensorMap m[7]; };
+
+// shared-memory tile geometry (floats).  Gu: own direction x.
+//   U  (TX+8) x (TY+8) origin (-4,-4) | V (TX+4) x (TY+8) origin (-4,-4) | Z TX x (TY+8) origin (0,-4)
+//   DX, DY, W (TX+8) x TY origin (-4,0) | P (TX+4) x TY origin (-4,0)
+#define GU_PU (TMA_TX + 8)
+#define GU_PV (TMA_TX + 4)
+#define GU_PZ (TMA_TX)
+#define GU_PD (TMA_TX + 8)
+#define GU_PP (TMA_TX + 4)
+#define GU_OFF_U 0
+#define GU_OFF_V (GU_OFF_U + GU_PU * (TMA_TY + 8))
+#define GU_OFF_Z (GU_OFF_V + GU_PV * (TMA_TY + 8))
+#define GU_OFF_DX (GU_OFF_Z + GU_PZ * (TMA_TY + 8))
+#define GU_OFF_DY (GU_OFF_DX + GU_PD * TMA_TY)
+#define GU_OFF_W (GU_OFF_DY + GU_PD * TMA_TY)
+#define GU_OFF_P (GU_OFF_W + GU_PD * TMA_TY)
+#define GU_STAGE (GU_OFF_P + GU_PP * TMA_TY)
+
+__global__ void __launch_bounds__(TMA_TX * TMA_TY, 3)
+k_gu_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaMaps7 tm, const float* __restrict__ u,
+         const float* __restrict__ v, const float* __restrict__ w, const float* __restrict__ p, float* __restrict__ G) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t bar[TMA_NST];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TMA_TX + tx;
+  const int i0 = blockIdx.x * TMA_TX + 1, j0 = blockIdx.y * TMA_TY + 1;
+  const int I0 = i0 + g.Hx - 1, J0 = j0 + g.Hy - 1;
+  const int i = i0 + tx, j = j0 + ty;
+  const bool valid = i <= g.Nx && j <= g.Ny;
+  const int PX = g.PX, n2 = g.n2, Nz = g.Nz;
+  const int q2 = id2(g, min(i, g.Nx), min(j, g.Ny));
+  const float eps = g.eps;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TMA_NST; s++) mbar_init(&bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int k) {   // level k -> stage (k-1) % NST   (called by thread 0 only)
+    const int s = (k - 1) % TMA_NST;
+    float* sm = smem + s * GU_STAGE;
+    const int K = k + g.Hz - 1;
+    mbar_expect_tx(&bar[s], GU_STAGE * sizeof(float));
+    tma_load_3d(sm + GU_OFF_U, &tm.m[0], &bar[s], I0 - 4, J0 - 4, K);
+    tma_load_3d(sm + GU_OFF_V, &tm.m[1], &bar[s], I0 - 4, J0 - 4, K);
+    tma_load_3d(sm + GU_OFF_Z, &tm.m[2], &bar[s], I0, J0 - 4, K);
+    tma_load_3d(sm + GU_OFF_DX, &tm.m[3], &bar[s], I0 - 4, J0, K);
+    tma_load_3d(sm + GU_OFF_DY, &tm.m[4], &bar[s], I0 - 4, J0, K);
+    tma_load_3d(sm + GU_OFF_W, &tm.m[5], &bar[s], I0 - 4, J0, K + 1);
+    tma_load_3d(sm + GU_OFF_P, &tm.m[6], &bar[s], I0 - 4, J0, K);
+  };
+  if (tid == 0) { issue(1); if (Nz >= 2) issue(2); }
+  // ---- hoisted 2-D data
+  const float m1 = g.dxfc[q2], rV0 = g.azfc[q2];
+  const float fbar = (g.fff[q2] + g.fff[q2 + PX]) * 0.5f;
+  const float mv00 = g.dxcf[q2 - 1], mv01 = g.dxcf[q2], mv10 = g.dxcf[q2 - 1 + PX], mv11 = g.dxcf[q2 + PX];
+  const float az0 = g.azcc[q2 - 2], az1 = g.azcc[q2 - 1], az2 = g.azcc[q2], az3 = g.azcc[q2 + 1];
+  const int kbc = g.kb[q2];
+  const int kgen = (int)g.knear[q2] + 1;
+  const int kzero = g.cond_diff ? (int)g.ksolid[q2] - 3 : 0;
+  // ---- vertical register window of u
+  size_t q3 = q2 + (size_t)n2 * g.Hz;
+  float WU[7];
+#pragma unroll
+  for (int m = 0; m < 7; m++) WU[m] = __ldg(u + q3 + (ptrdiff_t)(m - 3) * n2);
+  float Wb = 0.f;
+  const int ou = (ty + 4) * GU_PU + (tx + 4), ov = (ty + 4) * GU_PV + (tx + 4), oz = (ty + 4) * GU_PZ + tx;
+  const int od = ty * GU_PD + (tx + 4), op = ty * GU_PP + (tx + 4);
+  for (int k = 1; k <= Nz; k++, q3 += n2) {
+    const int s = (k - 1) % TMA_NST;
+    if (tid == 0 && k + 2 <= Nz) issue(k + 2);
+    mbar_wait(&bar[s], ((k - 1) / TMA_NST) & 1);
+    const float* sm = smem + s * GU_STAGE;
+    const float* U = sm + GU_OFF_U + ou; const float* V = sm + GU_OFF_V + ov; const float* Z = sm + GU_OFF_Z + oz;
+    const float* DX = sm + GU_OFF_DX + od; const float* DY = sm + GU_OFF_DY + od; const float* W = sm + GU_OFF_W + od;
+    const float* P = sm + GU_OFF_P + op;
+    float out = 0.f;
+    if (valid) {
+      if (k <= kzero) {
+        out = 0.f; Wb = 0.f;
+      } else if (k <= kgen) {
+        out = momentum_G_call3<0>(gp, u, v, w, p, i, j, k, &Wb);
+      } else {
+        const float dz = g.dzc[k + g.Hz - 1];
+        const float own0 = WU[3];
+        const bool lown = own0 > 0.f;
+        const float xm0 = mv00 * V[-1], xm1 = mv10 * V[GU_PV - 1];
+        const float x00 = mv01 * V[0], x01 = mv11 * V[GU_PV];
+        const float oavg = ((xm0 + xm1) * 0.5f + (x00 + x01) * 0.5f) * 0.5f;
+        const float ohat = oavg / m1;
+        float zq[6], zs[6], zr[6];
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+          const int b = m - 2;
+          zq[m] = Z[b * GU_PZ];
+          zs[m] = (U[(b - 1) * GU_PU] + U[b * GU_PU]) * 0.5f;
+          zr[m] = (V[b * GU_PV - 1] + V[b * GU_PV]) * 0.5f;
+        }
+        const float zR = ohat > 0.f ? weno5_vs(zq[0], zq[1], zq[2], zq[3], zq[4], zs[0], zs[1], zs[2], zs[3], zs[4], zr[0], zr[1], zr[2], zr[3], zr[4], eps)
+                                    : weno5_vs(zq[5], zq[4], zq[3], zq[2], zq[1], zs[5], zs[4], zs[3], zs[2], zs[1], zr[5], zr[4], zr[3], zr[2], zr[1], eps);
+        const float Hterm = -ohat * zR;
+        float dOw[6], dv[6], dK[6], sK[6];
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+          const int a = m - 3;
+          dOw[m] = DX[a];
+          dv[m] = DX[a] + DY[a];
+          const float o0 = U[a], o1 = U[a + 1];
+          dK[m] = o1 * o1 * 0.5f - o0 * o0 * 0.5f;
+          sK[m] = (o0 + o1) * 0.5f;
+        }
+        const float dvs = sym4(DY[-2], DY[-1], DY[0], DY[1], 2);
+        const float duR = weno5_fs_sel3(dOw, dv, lown, eps);
+        const float Phi = own0 * (dvs + duR);
+        const float dKo = weno5_fs_sel3(dK, sK, lown, eps);
+        float kc[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          const int b = m - 1;
+          const float t0 = V[b * GU_PV], tm_ = V[b * GU_PV - 1];
+          kc[m] = t0 * t0 * 0.5f - tm_ * tm_ * 0.5f;
+        }
+        const float Bterm = (dKo + sym4(kc[0], kc[1], kc[2], kc[3], 2)) / m1;
+        const int Bw = (g.immersed && k + 1 > Nz) ? 1 : 2;
+        const float wt = sym4(az0 * W[-2], az1 * W[-1], az2 * W[0], az3 * W[1], Bw);
+        const int Bz = zbuf(g, kbc, k + 1, 3);
+        const float Wt = wt * weno_sel_B3(WU[1], WU[2], WU[3], WU[4], WU[5], WU[6], Bz, wt > 0.f, eps);
+        const float Vterm = (1.f / (rV0 * dz)) * (Phi + (Wt - Wb));
+        Wb = Wt;
+        const float cor = -(fbar * oavg / m1);
+        const float dp = (P[0] - P[-1]) / m1;
+        out = -(Hterm + Vterm + Bterm) - cor - dp;
+      }
+      G[q3] = out;
+#pragma unroll
+      for (int m = 0; m < 6; m++) WU[m] = WU[m + 1];
+      WU[6] = __ldg(u + q3 + (size_t)4 * n2);
+    }
+    __syncthreads();   // every thread is done with stage s before it is refilled (two iterations from now)
+  }
+}
+
+// Gv: own direction y.  V (TX+8) x (TY+8) origin (-4,-4) | U (TX+8) x (TY+8) origin (-4,-4) | Z (TX+8) x TY origin (-4,0)
+//     DY, DX, W, P: TX x (TY+8) origin (0,-4)
+#define GV_PV (TMA_TX + 8)
+#define GV_PU (TMA_TX + 8)
+#define GV_PZ (TMA_TX + 8)
+#define GV_PD (TMA_TX)
+#define GV_OFF_V 0
+#define GV_OFF_U (GV_OFF_V + GV_PV * (TMA_TY + 8))
+#define GV_OFF_Z (GV_OFF_U + GV_PU * (TMA_TY + 8))
+#define GV_OFF_DY (GV_OFF_Z + GV_PZ * TMA_TY)
+#define GV_OFF_DX (GV_OFF_DY + GV_PD * (TMA_TY + 8))
+#define GV_OFF_W (GV_OFF_DX + GV_PD * (TMA_TY + 8))
+#define GV_OFF_P (GV_OFF_W + GV_PD * (TMA_TY + 8))
+#define GV_STAGE (GV_OFF_P + GV_PD * (TMA_TY + 8))
+
+__global__ void __launch_bounds__(TMA_TX * TMA_TY, 3)
+k_gv_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaMaps7 tm, const float* __restrict__ u,
+         const float* __restrict__ v, const float* __restrict__ w, const float* __restrict__ p, float* __restrict__ G) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t bar[TMA_NST];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TMA_TX + tx;
+  const int i0 = blockIdx.x * TMA_TX + 1, j0 = blockIdx.y * TMA_TY + 1;
+  const int I0 = i0 + g.Hx - 1, J0 = j0 + g.Hy - 1;
+  const int i = i0 + tx, j = j0 + ty;
+  const bool valid = i <= g.Nx && j <= g.Ny;
+  const int PX = g.PX, n2 = g.n2, Nz = g.Nz;
+  const int q2 = id2(g, min(i, g.Nx), min(j, g.Ny));
+  const float eps = g.eps;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TMA_NST; s++) mbar_init(&bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int k) {
+    const int s = (k - 1) % TMA_NST;
+    float* sm = smem + s * GV_STAGE;
+    const int K = k + g.Hz - 1;
+    mbar_expect_tx(&bar[s], GV_STAGE * sizeof(float));
+    tma_load_3d(sm + GV_OFF_V, &tm.m[0], &bar[s], I0 - 4, J0 - 4, K);
+    tma_load_3d(sm + GV_OFF_U, &tm.m[1], &bar[s], I0 - 4, J0 - 4, K);
+    tma_load_3d(sm + GV_OFF_Z, &tm.m[2], &bar[s], I0 - 4, J0, K);
+    tma_load_3d(sm + GV_OFF_DY, &tm.m[3], &bar[s], I0, J0 - 4, K);
+    tma_load_3d(sm + GV_OFF_DX, &tm.m[4], &bar[s], I0, J0 - 4, K);
+    tma_load_3d(sm + GV_OFF_W, &tm.m[5], &bar[s], I0, J0 - 4, K + 1);
+    tma_load_3d(sm + GV_OFF_P, &tm.m[6], &bar[s], I0, J0 - 4, K);
+  };
+  if (tid == 0) { issue(1); if (Nz >= 2) issue(2); }
+  const float m1 = g.dycf[q2], rV0 = g.azcf[q2];
+  const float fbar = (g.fff[q2] + g.fff[q2 + 1]) * 0.5f;
+  const float mu00 = g.dyfc[q2 - PX], mu01 = g.dyfc[q2 - PX + 1], mu10 = g.dyfc[q2], mu11 = g.dyfc[q2 + 1];
+  const float az0 = g.azcc[q2 - 2 * PX], az1 = g.azcc[q2 - PX], az2 = g.azcc[q2], az3 = g.azcc[q2 + PX];
+  const int kbc = g.kb[q2];
+  const int kgen = (int)g.knear[q2] + 1;
+  const int kzero = g.cond_diff ? (int)g.ksolid[q2] - 3 : 0;
+  size_t q3 = q2 + (size_t)n2 * g.Hz;
+  float WV[7];
+#pragma unroll
+  for (int m = 0; m < 7; m++) WV[m] = __ldg(v + q3 + (ptrdiff_t)(m - 3) * n2);
+  float Wb = 0.f;
+  const int ov = (ty + 4) * GV_PV + (tx + 4), ou = (ty + 4) * GV_PU + (tx + 4), oz = ty * GV_PZ + (tx + 4);
+  const int od = (ty + 4) * GV_PD + tx;
+  for (int k = 1; k <= Nz; k++, q3 += n2) {
+    const int s = (k - 1) % TMA_NST;
+    if (tid == 0 && k + 2 <= Nz) issue(k + 2);
+    mbar_wait(&bar[s], ((k - 1) / TMA_NST) & 1);
+    const float* sm = smem + s * GV_STAGE;
+    const float* V = sm + GV_OFF_V + ov; const float* U = sm + GV_OFF_U + ou; const float* Z = sm + GV_OFF_Z + oz;
+    const float* DY = sm + GV_OFF_DY + od; const float* DX = sm + GV_OFF_DX + od; const float* W = sm + GV_OFF_W + od;
+    const float* P = sm + GV_OFF_P + od;
+    float out = 0.f;
+    if (valid) {
+      if (k <= kzero) {
+        out = 0.f; Wb = 0.f;
+      } else if (k <= kgen) {
+        out = momentum_G_call3<1>(gp, v, u, w, p, i, j, k, &Wb);
+      } else {
+        const float dz = g.dzc[k + g.Hz - 1];
+        const float own0 = WV[3];
+        const bool lown = own0 > 0.f;
+        const float xm0 = mu00 * U[-GV_PU], xm1 = mu01 * U[-GV_PU + 1];
+        const float x00 = mu10 * U[0], x01 = mu11 * U[1];
+        const float oavg = ((xm0 + xm1) * 0.5f + (x00 + x01) * 0.5f) * 0.5f;
+        const float ohat = oavg / m1;
+        float zq[6], zs[6], zr[6];
+#pragma unroll
+        for (int m = 0; m < 6; m++) {           // window along x: cols i-2 .. i+3
+          const int b = m - 2;
+          zq[m] = Z[b];
+          zs[m] = (V[b - 1] + V[b]) * 0.5f;
+          zr[m] = (U[b - GV_PU] + U[b]) * 0.5f;
+        }
+        const float zR = ohat > 0.f ? weno5_vs(zq[0], zq[1], zq[2], zq[3], zq[4], zs[0], zs[1], zs[2], zs[3], zs[4], zr[0], zr[1], zr[2], zr[3], zr[4], eps)
+                                    : weno5_vs(zq[5], zq[4], zq[3], zq[2], zq[1], zs[5], zs[4], zs[3], zs[2], zs[1], zr[5], zr[4], zr[3], zr[2], zr[1], eps);
+        const float Hterm = ohat * zR;
+        float dOw[6], dv[6], dK[6], sK[6];
+#pragma unroll
+        for (int m = 0; m < 6; m++) {           // window along y: rows j-3 .. j+2
+          const int a = m - 3;
+          dOw[m] = DY[a * GV_PD];
+          dv[m] = DX[a * GV_PD] + DY[a * GV_PD];
+          const float o0 = V[a * GV_PV], o1 = V[(a + 1) * GV_PV];
+          dK[m] = o1 * o1 * 0.5f - o0 * o0 * 0.5f;
+          sK[m] = (o0 + o1) * 0.5f;
+        }
+        const float dus = sym4(DX[-2 * GV_PD], DX[-GV_PD], DX[0], DX[GV_PD], 2);
+        const float dvR = weno5_fs_sel3(dOw, dv, lown, eps);
+        const float Phi = own0 * (dus + dvR);
+        const float dKo = weno5_fs_sel3(dK, sK, lown, eps);
+        float kc[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {           // cols i-1 .. i+2
+          const int b = m - 1;
+          const float t0 = U[b], tm_ = U[b - GV_PU];
+          kc[m] = t0 * t0 * 0.5f - tm_ * tm_ * 0.5f;
+        }
+        const float Bterm = (dKo + sym4(kc[0], kc[1], kc[2], kc[3], 2)) / m1;
+        const int Bw = (g.immersed && k + 1 > Nz) ? 1 : 2;
+        const float wt = sym4(az0 * W[-2 * GV_PD], az1 * W[-GV_PD], az2 * W[0], az3 * W[GV_PD], Bw);
+        const int Bz = zbuf(g, kbc, k + 1, 3);
+        const float Wt = wt * weno_sel_B3(WV[1], WV[2], WV[3], WV[4], WV[5], WV[6], Bz, wt > 0.f, eps);
+        const float Vterm = (1.f / (rV0 * dz)) * (Phi + (Wt - Wb));
+        Wb = Wt;
+        const float cor = fbar * oavg / m1;
+        const float dp = (P[0] - P[-GV_PD]) / m1;
+        out = -(Hterm + Vterm + Bterm) - cor - dp;
+      }
+      G[q3] = out;
+#pragma unroll
+      for (int m = 0; m < 6; m++) WV[m] = WV[m + 1];
+      WV[6] = __ldg(v + q3 + (size_t)4 * n2);
+    }
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encoder() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+static bool make_map(const DevGrid& g, const float* base, int bx, int by, CUtensorMap* out) {
+  PFN_encodeTiled enc = get_encoder();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)g.PX, (cuuint64_t)g.PY, (cuuint64_t)g.PZ};
+  cuuint64_t strides[2] = {(cuuint64_t)g.PX * 4, (cuuint64_t)g.PX * g.PY * 4};
+  cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct TmaState { bool ready = false, ok = false; TmaMaps7 gu, gv; };
+static TmaState* tma_state(Handle* h) {
+  if (!h->tma) h->tma = new TmaState();
+  TmaState* t = (TmaState*)h->tma;
+  if (t->ready) return t;
+  t->ready = true;
+  const DevGrid& g = h->g;
+  if (g.PX % 4) return t;   // TMA needs 16-byte row pitch
+  const int TX = TMA_TX, TY = TMA_TY;
+  bool ok = true;
+  ok &= make_map(g, h->f.u, TX + 8, TY + 8, &t->gu.m[0]);
+  ok &= make_map(g, h->f.v, TX + 4, TY + 8, &t->gu.m[1]);
+  ok &= make_map(g, h->zeta, TX, TY + 8, &t->gu.m[2]);
+  ok &= make_map(g, h->dxU, TX + 8, TY, &t->gu.m[3]);
+  ok &= make_map(g, h->dyV, TX + 8, TY, &t->gu.m[4]);
+  ok &= make_map(g, h->f.w, TX + 8, TY, &t->gu.m[5]);
+  ok &= make_map(g, h->f.p, TX + 4, TY, &t->gu.m[6]);
+  ok &= make_map(g, h->f.v, TX + 8, TY + 8, &t->gv.m[0]);
+  ok &= make_map(g, h->f.u, TX + 8, TY + 8, &t->gv.m[1]);
+  ok &= make_map(g, h->zeta, TX + 8, TY, &t->gv.m[2]);
+  ok &= make_map(g, h->dyV, TX, TY + 8, &t->gv.m[3]);
+  ok &= make_map(g, h->dxU, TX, TY + 8, &t->gv.m[4]);
+  ok &= make_map(g, h->f.w, TX, TY + 8, &t->gv.m[5]);
+  ok &= make_map(g, h->f.p, TX, TY + 8, &t->gv.m[6]);
+  if (ok) {
+    ok &= cudaFuncSetAttribute(k_gu_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GU_STAGE * (int)sizeof(float)) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(k_gv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GV_STAGE * (int)sizeof(float)) == cudaSuccess;
+  }
+  t->ok = ok;
+  return t;
+}
+bool tma_available(Handle* h) { return tma_state(h)->ok; }
+void tma_free(Handle* h) { delete (TmaState*)h->tma; h->tma = nullptr; }
+
+void launch_momentum_tendency_tma(Handle* h) {
+  TmaState* t = tma_state(h);
+  const DevGrid& g = h->g;
+  dim3 b(TMA_TX, TMA_TY), gr((g.Nx + TMA_TX - 1) / TMA_TX, (g.Ny + TMA_TY - 1) / TMA_TY);
+  k_gu_tma<<<gr, b, TMA_NST * GU_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gu, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[0]);
+  h->count_launch();
+  k_gv_tma<<<gr, b, TMA_NST * GV_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gv, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[1]);
+  h->count_launch();
+}
