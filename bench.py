@@ -34,6 +34,8 @@ WORKLOADS = {
     # name: (grid_type, Nx, Ny, Nz, dt)
     "tripolar_quarter_degree": ("gaussian_islands", 1440, 600, 50, 60.0),
     "latlon_128x64x8": ("simple_lat_lon", 128, 64, 8, 60.0),
+    "tripolar_flat": ("tripolar", 1440, 600, 50, 60.0),              # profiling aid: no bathymetry => fast path only
+    "latlon_1440x600x50": ("simple_lat_lon", 1440, 600, 50, 60.0),
 }
 ALGORITHMIC_BYTES_PER_CELL_STEP = 104     # 26 Float32 words of compulsory 3-D traffic
 # algorithmic bytes per cell of one launch of each tendency kernel (DESIGN.md "kernels")

@@ -4,9 +4,10 @@
 // utilisation at 16-20 % occupancy — every level starts with ~40 dependent global loads per thread and there are
 // too few warps to hide them.  Here the loads leave the instruction stream altogether:
 //   * a CTA owns a 32 x 8 tile of columns and marches k = 1..Nz, one cell per thread;
-//   * for every level one elected thread issues 3-D TMA box loads (cp.async.bulk.tensor) of the halo'd tiles of
-//     u, v, zeta, dxU, dyV, w(k+1) and p into a 3-stage shared-memory ring, two levels ahead, completion tracked by
-//     one mbarrier per stage (expect_tx / complete_tx);
+//   * a dedicated producer warp issues, level by level, 3-D TMA box loads (cp.async.bulk.tensor) of the halo'd
+//     tiles of u, v, zeta, dxU, dyV, w(k+1) and p into a 4-stage shared-memory ring; a "full" mbarrier per stage
+//     tracks the bytes (expect_tx / complete_tx), an "empty" mbarrier per stage is armed by the consumer warps, so
+//     there is no CTA-wide barrier in the k loop and warps drift up to three levels apart;
 //   * the arithmetic reads its stencils from shared memory with immediate offsets (no address arithmetic, no
 //     dependence on L1 hit rates), the vertical stencil of the own velocity lives in a register window, the
 //     vertical momentum flux is carried from face to face;
@@ -20,7 +21,13 @@
 
 #define TMA_TX 32
 #define TMA_TY 8
-#define TMA_NST 3
+#ifndef TMA_MINB
+#define TMA_MINB 2
+#endif
+#ifndef TMA_NST
+#define TMA_NST 4
+#endif
+#define TMA_CW (TMA_TY)          // consumer warps (one per tile row); warp TMA_TY is the TMA producer
 
 // ----------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -29,6 +36,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
   uint32_t ok;
@@ -57,8 +67,7 @@ __device__ __forceinline__ float weno_sel_B3(float q0, float q1, float q2, float
   return left ? q2 : q3;
 }
 __device__ __forceinline__ float weno5_fs_sel3(const float (&q)[6], const float (&s)[6], bool left, float eps) {
-  return left ? weno5_fs(q[0], q[1], q[2], q[3], q[4], s[0], s[1], s[2], s[3], s[4], eps)
-              : weno5_fs(q[5], q[4], q[3], q[2], q[1], s[5], s[4], s[3], s[2], s[1], eps);
+  return weno5_fs_selq(q, s, left, eps);
 }
 
 struct TmaMaps7 { CUtensorMap m[7]; };
@@ -80,11 +89,11 @@ struct TmaMaps7 { CUtensorMap m[7]; };
 #define GU_OFF_P (GU_OFF_W + GU_PD * TMA_TY)
 #define GU_STAGE (GU_OFF_P + GU_PP * TMA_TY)
 
-__global__ void __launch_bounds__(TMA_TX * TMA_TY, 3)
+__global__ void __launch_bounds__(TMA_TX * (TMA_TY + 1), TMA_MINB)
 k_gu_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaMaps7 tm, const float* __restrict__ u,
          const float* __restrict__ v, const float* __restrict__ w, const float* __restrict__ p, float* __restrict__ G) {
   extern __shared__ __align__(128) float smem[];
-  __shared__ uint64_t bar[TMA_NST];
+  __shared__ uint64_t bar[TMA_NST], ebar[TMA_NST];   // full (TMA landed) / empty (all consumer warps done) per stage
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TMA_TX + tx;
   const int i0 = blockIdx.x * TMA_TX + 1, j0 = blockIdx.y * TMA_TY + 1;
   const int I0 = i0 + g.Hx - 1, J0 = j0 + g.Hy - 1;
@@ -95,7 +104,7 @@ k_gu_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
   const float eps = g.eps;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < TMA_NST; s++) mbar_init(&bar[s], 1);
+    for (int s = 0; s < TMA_NST; s++) { mbar_init(&bar[s], 1); mbar_init(&ebar[s], TMA_CW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -112,14 +121,21 @@ k_gu_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
     tma_load_3d(sm + GU_OFF_W, &tm.m[5], &bar[s], I0 - 4, J0, K + 1);
     tma_load_3d(sm + GU_OFF_P, &tm.m[6], &bar[s], I0 - 4, J0, K);
   };
-  if (tid == 0) { issue(1); if (Nz >= 2) issue(2); }
+  if (ty == TMA_TY) {   // ===== producer warp: keeps the ring full, one elected lane issues the TMA loads
+    if (tx == 0)
+      for (int k = 1; k <= Nz; k++) {
+        if (k > TMA_NST) mbar_wait(&ebar[(k - 1) % TMA_NST], (((k - 1) / TMA_NST) - 1) & 1);
+        issue(k);
+      }
+    return;
+  }
   // ---- hoisted 2-D data
   const float m1 = g.dxfc[q2], rV0 = g.azfc[q2];
   const float fbar = (g.fff[q2] + g.fff[q2 + PX]) * 0.5f;
   const float mv00 = g.dxcf[q2 - 1], mv01 = g.dxcf[q2], mv10 = g.dxcf[q2 - 1 + PX], mv11 = g.dxcf[q2 + PX];
   const float az0 = g.azcc[q2 - 2], az1 = g.azcc[q2 - 1], az2 = g.azcc[q2], az3 = g.azcc[q2 + 1];
   const int kbc = g.kb[q2];
-  const int kgen = (int)g.knear[q2] + 1;
+  const int kgen = (int)g.knear[q2];   // the fast path needs level k itself clear; the bottom-face flux is carried
   const int kzero = g.cond_diff ? (int)g.ksolid[q2] - 3 : 0;
   // ---- vertical register window of u
   size_t q3 = q2 + (size_t)n2 * g.Hz;
@@ -131,7 +147,6 @@ k_gu_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
   const int od = ty * GU_PD + (tx + 4), op = ty * GU_PP + (tx + 4);
   for (int k = 1; k <= Nz; k++, q3 += n2) {
     const int s = (k - 1) % TMA_NST;
-    if (tid == 0 && k + 2 <= Nz) issue(k + 2);
     mbar_wait(&bar[s], ((k - 1) / TMA_NST) & 1);
     const float* sm = smem + s * GU_STAGE;
     const float* U = sm + GU_OFF_U + ou; const float* V = sm + GU_OFF_V + ov; const float* Z = sm + GU_OFF_Z + oz;
@@ -159,8 +174,7 @@ k_gu_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
           zs[m] = (U[(b - 1) * GU_PU] + U[b * GU_PU]) * 0.5f;
           zr[m] = (V[b * GU_PV - 1] + V[b * GU_PV]) * 0.5f;
         }
-        const float zR = ohat > 0.f ? weno5_vs(zq[0], zq[1], zq[2], zq[3], zq[4], zs[0], zs[1], zs[2], zs[3], zs[4], zr[0], zr[1], zr[2], zr[3], zr[4], eps)
-                                    : weno5_vs(zq[5], zq[4], zq[3], zq[2], zq[1], zs[5], zs[4], zs[3], zs[2], zs[1], zr[5], zr[4], zr[3], zr[2], zr[1], eps);
+        const float zR = weno5_vs_selq(zq, zs, zr, ohat > 0.f, eps);
         const float Hterm = -ohat * zR;
         float dOw[6], dv[6], dK[6], sK[6];
 #pragma unroll
@@ -199,7 +213,8 @@ k_gu_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
       for (int m = 0; m < 6; m++) WU[m] = WU[m + 1];
       WU[6] = __ldg(u + q3 + (size_t)4 * n2);
     }
-    __syncthreads();   // every thread is done with stage s before it is refilled (two iterations from now)
+    __syncwarp();
+    if (tx == 0) mbar_arrive(&ebar[s]);   // this warp is done with stage s
   }
 }
 
@@ -218,11 +233,11 @@ k_gu_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
 #define GV_OFF_P (GV_OFF_W + GV_PD * (TMA_TY + 8))
 #define GV_STAGE (GV_OFF_P + GV_PD * (TMA_TY + 8))
 
-__global__ void __launch_bounds__(TMA_TX * TMA_TY, 3)
+__global__ void __launch_bounds__(TMA_TX * (TMA_TY + 1), TMA_MINB)
 k_gv_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaMaps7 tm, const float* __restrict__ u,
          const float* __restrict__ v, const float* __restrict__ w, const float* __restrict__ p, float* __restrict__ G) {
   extern __shared__ __align__(128) float smem[];
-  __shared__ uint64_t bar[TMA_NST];
+  __shared__ uint64_t bar[TMA_NST], ebar[TMA_NST];   // full (TMA landed) / empty (all consumer warps done) per stage
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TMA_TX + tx;
   const int i0 = blockIdx.x * TMA_TX + 1, j0 = blockIdx.y * TMA_TY + 1;
   const int I0 = i0 + g.Hx - 1, J0 = j0 + g.Hy - 1;
@@ -233,7 +248,7 @@ k_gv_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
   const float eps = g.eps;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < TMA_NST; s++) mbar_init(&bar[s], 1);
+    for (int s = 0; s < TMA_NST; s++) { mbar_init(&bar[s], 1); mbar_init(&ebar[s], TMA_CW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -250,13 +265,20 @@ k_gv_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
     tma_load_3d(sm + GV_OFF_W, &tm.m[5], &bar[s], I0, J0 - 4, K + 1);
     tma_load_3d(sm + GV_OFF_P, &tm.m[6], &bar[s], I0, J0 - 4, K);
   };
-  if (tid == 0) { issue(1); if (Nz >= 2) issue(2); }
+  if (ty == TMA_TY) {
+    if (tx == 0)
+      for (int k = 1; k <= Nz; k++) {
+        if (k > TMA_NST) mbar_wait(&ebar[(k - 1) % TMA_NST], (((k - 1) / TMA_NST) - 1) & 1);
+        issue(k);
+      }
+    return;
+  }
   const float m1 = g.dycf[q2], rV0 = g.azcf[q2];
   const float fbar = (g.fff[q2] + g.fff[q2 + 1]) * 0.5f;
   const float mu00 = g.dyfc[q2 - PX], mu01 = g.dyfc[q2 - PX + 1], mu10 = g.dyfc[q2], mu11 = g.dyfc[q2 + 1];
   const float az0 = g.azcc[q2 - 2 * PX], az1 = g.azcc[q2 - PX], az2 = g.azcc[q2], az3 = g.azcc[q2 + PX];
   const int kbc = g.kb[q2];
-  const int kgen = (int)g.knear[q2] + 1;
+  const int kgen = (int)g.knear[q2];   // the fast path needs level k itself clear; the bottom-face flux is carried
   const int kzero = g.cond_diff ? (int)g.ksolid[q2] - 3 : 0;
   size_t q3 = q2 + (size_t)n2 * g.Hz;
   float WV[7];
@@ -267,7 +289,6 @@ k_gv_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
   const int od = (ty + 4) * GV_PD + tx;
   for (int k = 1; k <= Nz; k++, q3 += n2) {
     const int s = (k - 1) % TMA_NST;
-    if (tid == 0 && k + 2 <= Nz) issue(k + 2);
     mbar_wait(&bar[s], ((k - 1) / TMA_NST) & 1);
     const float* sm = smem + s * GV_STAGE;
     const float* V = sm + GV_OFF_V + ov; const float* U = sm + GV_OFF_U + ou; const float* Z = sm + GV_OFF_Z + oz;
@@ -295,8 +316,7 @@ k_gv_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
           zs[m] = (V[b - 1] + V[b]) * 0.5f;
           zr[m] = (U[b - GV_PU] + U[b]) * 0.5f;
         }
-        const float zR = ohat > 0.f ? weno5_vs(zq[0], zq[1], zq[2], zq[3], zq[4], zs[0], zs[1], zs[2], zs[3], zs[4], zr[0], zr[1], zr[2], zr[3], zr[4], eps)
-                                    : weno5_vs(zq[5], zq[4], zq[3], zq[2], zq[1], zs[5], zs[4], zs[3], zs[2], zs[1], zr[5], zr[4], zr[3], zr[2], zr[1], eps);
+        const float zR = weno5_vs_selq(zq, zs, zr, ohat > 0.f, eps);
         const float Hterm = ohat * zR;
         float dOw[6], dv[6], dK[6], sK[6];
 #pragma unroll
@@ -335,7 +355,8 @@ k_gv_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
       for (int m = 0; m < 6; m++) WV[m] = WV[m + 1];
       WV[6] = __ldg(v + q3 + (size_t)4 * n2);
     }
-    __syncthreads();
+    __syncwarp();
+    if (tx == 0) mbar_arrive(&ebar[s]);
   }
 }
 
@@ -401,7 +422,7 @@ void tma_free(Handle* h) { delete (TmaState*)h->tma; h->tma = nullptr; }
 void launch_momentum_tendency_tma(Handle* h) {
   TmaState* t = tma_state(h);
   const DevGrid& g = h->g;
-  dim3 b(TMA_TX, TMA_TY), gr((g.Nx + TMA_TX - 1) / TMA_TX, (g.Ny + TMA_TY - 1) / TMA_TY);
+  dim3 b(TMA_TX, TMA_TY + 1), gr((g.Nx + TMA_TX - 1) / TMA_TX, (g.Ny + TMA_TY - 1) / TMA_TY);
   k_gu_tma<<<gr, b, TMA_NST * GU_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gu, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[0]);
   h->count_launch();
   k_gv_tma<<<gr, b, TMA_NST * GV_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gv, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[1]);

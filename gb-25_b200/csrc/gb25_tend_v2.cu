@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128) k_tracer_tendency_v2(DevGrid g, const Dev
   for (int c = 0; c < NC; c++) {
     dxs[c] = g.dxcf[q2 + c]; dxn[c] = g.dxcf[q2 + PX + c]; az[c] = g.azcc[q2 + c];
     kbc[c] = g.kb[q2 + c];
-    kgen = max(kgen, (int)g.knear[q2 + c] + 1);
+    kgen = max(kgen, (int)g.knear[q2 + c]);   // level k itself must be clear; the bottom-face flux is carried
     kzero = min(kzero, (int)g.ksolid[q2 + c] - 3);
   }
   // ---- vertical register window: WT[c][m] = T(i0+c, j, k-3+m)
@@ -241,8 +241,7 @@ __device__ __forceinline__ void ldrow(const float* p, float (&o)[2 * NP]) {
   for (int b = 0; b < NP; b++) { const float2 a = ld2(p + 2 * b); o[2 * b] = a.x; o[2 * b + 1] = a.y; }
 }
 __device__ __forceinline__ float weno5_fs_sel(const float (&q)[6], const float (&s)[6], bool left, float eps) {
-  return left ? weno5_fs(q[0], q[1], q[2], q[3], q[4], s[0], s[1], s[2], s[3], s[4], eps)
-              : weno5_fs(q[5], q[4], q[3], q[2], q[1], s[5], s[4], s[3], s[2], s[1], eps);
+  return weno5_fs_selq(q, s, left, eps);
 }
 
 // ---- Gu: own direction = x (contiguous), cross = y
@@ -268,7 +267,7 @@ __global__ void __launch_bounds__(128) k_gu_v2(DevGrid g, const DevGrid* __restr
     rV0[c] = g.azfc[q2 + c];
     fbar[c] = (g.fff[q2 + c] + g.fff[q2 + c + PX]) * 0.5f;
     kbc[c] = g.kb[q2 + c];
-    kgen = max(kgen, (int)g.knear[q2 + c] + 1);
+    kgen = max(kgen, (int)g.knear[q2 + c]);   // level k itself must be clear; the bottom-face flux is carried
   }
 #pragma unroll
   for (int c = 0; c <= NC; c++) { mv[0][c] = g.dxcf[q2 + c - 1]; mv[1][c] = g.dxcf[q2 + c - 1 + PX]; }
@@ -341,8 +340,7 @@ __global__ void __launch_bounds__(128) k_gu_v2(DevGrid g, const DevGrid* __restr
           zs[m] = (uy[m][c] + uy[m + 1][c]) * 0.5f;
           zr[m] = (vy[m][1 + c] + vy[m][2 + c]) * 0.5f;
         }
-        const float zR = ohat > 0.f ? weno5_vs(zq[0], zq[1], zq[2], zq[3], zq[4], zs[0], zs[1], zs[2], zs[3], zs[4], zr[0], zr[1], zr[2], zr[3], zr[4], eps)
-                                    : weno5_vs(zq[5], zq[4], zq[3], zq[2], zq[1], zs[5], zs[4], zs[3], zs[2], zs[1], zr[5], zr[4], zr[3], zr[2], zr[1], eps);
+        const float zR = weno5_vs_selq(zq, zs, zr, ohat > 0.f, eps);
         const float Hterm = -ohat * zR;
         // divergence flux and kinetic-energy gradient along x (cells i-3 .. i+2  <->  dxr[1+c .. 6+c])
         float dOw[6], dv[6], dK[6], sK[6];
@@ -413,7 +411,7 @@ __global__ void __launch_bounds__(128) k_gv_v2(DevGrid g, const DevGrid* __restr
     rV0[c] = g.azcf[q2 + c];
     fbar[c] = (g.fff[q2 + c] + g.fff[q2 + c + 1]) * 0.5f;
     kbc[c] = g.kb[q2 + c];
-    kgen = max(kgen, (int)g.knear[q2 + c] + 1);
+    kgen = max(kgen, (int)g.knear[q2 + c]);   // level k itself must be clear; the bottom-face flux is carried
 #pragma unroll
     for (int m = 0; m < 4; m++) azw[m][c] = g.azcc[q2 + c + (m - 2) * PX];
   }
@@ -486,8 +484,7 @@ __global__ void __launch_bounds__(128) k_gv_v2(DevGrid g, const DevGrid* __restr
           zs[m] = (vr[1 + c + m] + vr[2 + c + m]) * 0.5f;   // (v(i+b-1, j) + v(i+b, j)) / 2
           zr[m] = (us[c + m] + un[c + m]) * 0.5f;            // (u(i+b, j-1) + u(i+b, j)) / 2
         }
-        const float zR = ohat > 0.f ? weno5_vs(zq[0], zq[1], zq[2], zq[3], zq[4], zs[0], zs[1], zs[2], zs[3], zs[4], zr[0], zr[1], zr[2], zr[3], zr[4], eps)
-                                    : weno5_vs(zq[5], zq[4], zq[3], zq[2], zq[1], zs[5], zs[4], zs[3], zs[2], zs[1], zr[5], zr[4], zr[3], zr[2], zr[1], eps);
+        const float zR = weno5_vs_selq(zq, zs, zr, ohat > 0.f, eps);
         const float Hterm = ohat * zR;
         float dOw[6], dv[6], dK[6], sK[6];
 #pragma unroll

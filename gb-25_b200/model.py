@@ -123,6 +123,8 @@ class HydrostaticFreeSurfaceModel(ModelBase):
 def make_grid(Nx, Ny, Nz, halo=(8, 8, 8), grid_type="simple_lat_lon"):
     if grid_type in ("gaussian_islands", ":gaussian_islands"):
         return _grids.gaussian_islands_tripolar_grid(Nx, Ny, Nz, halo)
+    if grid_type in ("tripolar", ":tripolar"):          # TripolarGrid without bathymetry (profiling aid)
+        return _grids.tripolar_grid(Nx, Ny, Nz, halo)
     if grid_type in ("simple_lat_lon", ":simple_lat_lon"):
         return _grids.simple_latitude_longitude_grid(Nx, Ny, Nz, halo)
     raise ValueError(f"grid_type={grid_type} must be :gaussian_islands or :simple_lat_lon.")
