@@ -178,6 +178,31 @@ static int build_immersed_products(Handle* h, const gb25_grid* grid) {
   if ((rc = upload(h, cy2.data(), n2, &h->g.cy2))) return rc;
   if ((rc = upload(h, knear.data(), n2, &h->g.knear))) return rc;
   if ((rc = upload(h, ksolid.data(), n2, &h->g.ksolid))) return rc;
+  // pair-based level ranges and the list of generic cells (see DevGrid)
+  std::vector<short> kgen2(n2, 0), kzero2(n2, 0);
+  std::vector<int> glist;
+  for (int J = 0; J < PY; J++)
+    for (int I = 0; I < PX; I++) {
+      const int q = I + PX * J;
+      const int i = I - c.Hx + 1;
+      const int Ip = (i >= 1) ? I - ((i - 1) & 1) : I;          // first column of the aligned pair
+      const int q0 = Ip + PX * J, q1 = std::min(Ip + 1, PX - 1) + PX * J;
+      const int kg = std::min((int)std::max(knear[q0], knear[q1]), c.Nz);
+      int kz = c.cond_diff ? std::min((int)ksolid[q0], (int)ksolid[q1]) - 3 : 0;
+      kz = std::max(std::min(kz, kg), 0);
+      kgen2[q] = (short)kg; kzero2[q] = (short)kz;
+    }
+  for (int j = 1; j <= c.Ny; j++)
+    for (int k = 1; k <= c.Nz; k++)
+      for (int i = 1; i <= c.Nx; i++) {
+        const int q = (i + c.Hx - 1) + PX * (j + c.Hy - 1);
+        if (k > kzero2[q] && k <= kgen2[q]) glist.push_back(q + n2 * (k + c.Hz - 1));
+      }
+  if ((rc = upload(h, kgen2.data(), n2, &h->g.kgen2))) return rc;
+  if ((rc = upload(h, kzero2.data(), n2, &h->g.kzero2))) return rc;
+  h->g.nglist = (int)glist.size();
+  if (glist.empty()) glist.push_back(0);
+  if ((rc = upload(h, glist.data(), glist.size(), &h->g.glist))) return rc;
   if ((rc = upload(h, Hfc.data(), n2, &h->g.Hfc))) return rc;
   if ((rc = upload(h, Hcf.data(), n2, &h->g.Hcf))) return rc;
   return GB25_OK;
@@ -286,7 +311,7 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     h->allocs.push_back(*sp);
     CKC(ckcuda(cudaMemsetAsync(*sp, 0, n3 * sizeof(float), h->stream), "cudaMemset"));
   }
-  for (float** sp : {&h->us2, &h->vs2}) {
+  for (float** sp : {&h->us2, &h->vs2, &h->carry[0], &h->carry[1], &h->carry[2], &h->carry[3]}) {
     cudaError_t ce = cudaMalloc(sp, n2 * sizeof(float));
     if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc scratch: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
     h->allocs.push_back(*sp);

@@ -44,7 +44,8 @@ struct gb25_handle {
   float* field_ptr[GB25_FIELD_COUNT];
   // scratch 3-D arrays shared by the v2 kernels: vorticity (F,F,C), delta_x(Ax u) and delta_y(Ay v) at (C,C,C)
   float *zeta = nullptr, *dxU = nullptr, *dyV = nullptr;
-  float *us2 = nullptr, *vs2 = nullptr;   // 2-D: column sums of the AB2-updated, masked velocities (fused path)
+  float *us2 = nullptr, *vs2 = nullptr;
+  float* carry[4] = {nullptr, nullptr, nullptr, nullptr};   // 2-D: vertical flux through the top face of the topmost generic cell (u, v, T, S)   // 2-D: column sums of the AB2-updated, masked velocities (fused path)
   // clock (model.clock)
   double time = 0.0;
   long iteration = 0;
@@ -94,6 +95,7 @@ void launch_tracer_tendency_v2(Handle* h);   // gb25_tend_v2.cu
 void launch_momentum_tendency_v1(Handle* h);
 void launch_momentum_tendency_v2(Handle* h);  // gb25_tend_v2.cu
 void launch_aux_columns(Handle* h);
+void launch_generic_list(Handle* h, bool momentum, bool tracers);   // gb25_tend_v2.cu
 void launch_momentum_tendency_tma(Handle* h);   // gb25_tend_tma.cu
 bool tma_available(Handle* h);
 void tma_free(Handle* h);           // gb25_tend_v2.cu: w + zeta + flux divergences in one column pass

@@ -91,7 +91,8 @@ struct TmaMaps7 { CUtensorMap m[7]; };
 
 __global__ void __launch_bounds__(TMA_TX * (TMA_TY + 1), TMA_MINB)
 k_gu_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaMaps7 tm, const float* __restrict__ u,
-         const float* __restrict__ v, const float* __restrict__ w, const float* __restrict__ p, float* __restrict__ G) {
+         const float* __restrict__ v, const float* __restrict__ w, const float* __restrict__ p, float* __restrict__ G,
+         const float* __restrict__ carry) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar[TMA_NST], ebar[TMA_NST];   // full (TMA landed) / empty (all consumer warps done) per stage
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TMA_TX + tx;
@@ -135,8 +136,7 @@ k_gu_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
   const float mv00 = g.dxcf[q2 - 1], mv01 = g.dxcf[q2], mv10 = g.dxcf[q2 - 1 + PX], mv11 = g.dxcf[q2 + PX];
   const float az0 = g.azcc[q2 - 2], az1 = g.azcc[q2 - 1], az2 = g.azcc[q2], az3 = g.azcc[q2 + 1];
   const int kbc = g.kb[q2];
-  const int kgen = (int)g.knear[q2];   // the fast path needs level k itself clear; the bottom-face flux is carried
-  const int kzero = g.cond_diff ? (int)g.ksolid[q2] - 3 : 0;
+  const int kgen = g.kgen2[q2], kzero = g.kzero2[q2];   // generic cells (kzero < k <= kgen) belong to k_generic_list
   // ---- vertical register window of u
   size_t q3 = q2 + (size_t)n2 * g.Hz;
   float WU[7];
@@ -153,12 +153,14 @@ k_gu_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
     const float* DX = sm + GU_OFF_DX + od; const float* DY = sm + GU_OFF_DY + od; const float* W = sm + GU_OFF_W + od;
     const float* P = sm + GU_OFF_P + op;
     float out = 0.f;
+    bool skip = false;
     if (valid) {
       if (k <= kzero) {
         out = 0.f; Wb = 0.f;
       } else if (k <= kgen) {
-        out = momentum_G_call3<0>(gp, u, v, w, p, i, j, k, &Wb);
+        skip = true;
       } else {
+        if (k == kgen + 1 && kgen > 0) Wb = carry[q2];
         const float dz = g.dzc[k + g.Hz - 1];
         const float own0 = WU[3];
         const bool lown = own0 > 0.f;
@@ -208,7 +210,7 @@ k_gu_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
         const float dp = (P[0] - P[-1]) / m1;
         out = -(Hterm + Vterm + Bterm) - cor - dp;
       }
-      G[q3] = out;
+      if (!skip) G[q3] = out;
 #pragma unroll
       for (int m = 0; m < 6; m++) WU[m] = WU[m + 1];
       WU[6] = __ldg(u + q3 + (size_t)4 * n2);
@@ -235,7 +237,8 @@ k_gu_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
 
 __global__ void __launch_bounds__(TMA_TX * (TMA_TY + 1), TMA_MINB)
 k_gv_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaMaps7 tm, const float* __restrict__ u,
-         const float* __restrict__ v, const float* __restrict__ w, const float* __restrict__ p, float* __restrict__ G) {
+         const float* __restrict__ v, const float* __restrict__ w, const float* __restrict__ p, float* __restrict__ G,
+         const float* __restrict__ carry) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar[TMA_NST], ebar[TMA_NST];   // full (TMA landed) / empty (all consumer warps done) per stage
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TMA_TX + tx;
@@ -278,8 +281,7 @@ k_gv_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
   const float mu00 = g.dyfc[q2 - PX], mu01 = g.dyfc[q2 - PX + 1], mu10 = g.dyfc[q2], mu11 = g.dyfc[q2 + 1];
   const float az0 = g.azcc[q2 - 2 * PX], az1 = g.azcc[q2 - PX], az2 = g.azcc[q2], az3 = g.azcc[q2 + PX];
   const int kbc = g.kb[q2];
-  const int kgen = (int)g.knear[q2];   // the fast path needs level k itself clear; the bottom-face flux is carried
-  const int kzero = g.cond_diff ? (int)g.ksolid[q2] - 3 : 0;
+  const int kgen = g.kgen2[q2], kzero = g.kzero2[q2];   // generic cells (kzero < k <= kgen) belong to k_generic_list
   size_t q3 = q2 + (size_t)n2 * g.Hz;
   float WV[7];
 #pragma unroll
@@ -295,12 +297,14 @@ k_gv_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
     const float* DY = sm + GV_OFF_DY + od; const float* DX = sm + GV_OFF_DX + od; const float* W = sm + GV_OFF_W + od;
     const float* P = sm + GV_OFF_P + od;
     float out = 0.f;
+    bool skip = false;
     if (valid) {
       if (k <= kzero) {
         out = 0.f; Wb = 0.f;
       } else if (k <= kgen) {
-        out = momentum_G_call3<1>(gp, v, u, w, p, i, j, k, &Wb);
+        skip = true;
       } else {
+        if (k == kgen + 1 && kgen > 0) Wb = carry[q2];
         const float dz = g.dzc[k + g.Hz - 1];
         const float own0 = WV[3];
         const bool lown = own0 > 0.f;
@@ -350,7 +354,7 @@ k_gv_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
         const float dp = (P[0] - P[-GV_PD]) / m1;
         out = -(Hterm + Vterm + Bterm) - cor - dp;
       }
-      G[q3] = out;
+      if (!skip) G[q3] = out;
 #pragma unroll
       for (int m = 0; m < 6; m++) WV[m] = WV[m + 1];
       WV[6] = __ldg(v + q3 + (size_t)4 * n2);
@@ -423,8 +427,8 @@ void launch_momentum_tendency_tma(Handle* h) {
   TmaState* t = tma_state(h);
   const DevGrid& g = h->g;
   dim3 b(TMA_TX, TMA_TY + 1), gr((g.Nx + TMA_TX - 1) / TMA_TX, (g.Ny + TMA_TY - 1) / TMA_TY);
-  k_gu_tma<<<gr, b, TMA_NST * GU_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gu, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[0]);
+  k_gu_tma<<<gr, b, TMA_NST * GU_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gu, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[0], h->carry[0]);
   h->count_launch();
-  k_gv_tma<<<gr, b, TMA_NST * GV_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gv, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[1]);
+  k_gv_tma<<<gr, b, TMA_NST * GV_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gv, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[1], h->carry[1]);
   h->count_launch();
 }

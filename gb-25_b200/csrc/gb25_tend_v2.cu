@@ -50,12 +50,14 @@ template <int NC>
 __global__ void __launch_bounds__(128) k_tracer_tendency_v2(DevGrid g, const DevGrid* __restrict__ gp, const float* __restrict__ u,
                                                              const float* __restrict__ v, const float* __restrict__ w,
                                                              const float* __restrict__ T0, const float* __restrict__ T1,
-                                                             float* __restrict__ G0, float* __restrict__ G1) {
+                                                             float* __restrict__ G0, float* __restrict__ G1,
+                                                             const float* __restrict__ carry0, const float* __restrict__ carry1) {
   const int i0 = NC * (blockIdx.x * blockDim.x + threadIdx.x) + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
   if (i0 > g.Nx || j > g.Ny) return;
   const float* __restrict__ T = blockIdx.z == 0 ? T0 : T1;
   float* __restrict__ GT = blockIdx.z == 0 ? G0 : G1;
+  const float* __restrict__ carry = blockIdx.z == 0 ? carry0 : carry1;
   const int PX = g.PX, n2 = g.n2, Nz = g.Nz;
   const int q2 = id2(g, i0, j);
   const float eps = g.eps;
@@ -70,9 +72,8 @@ __global__ void __launch_bounds__(128) k_tracer_tendency_v2(DevGrid g, const Dev
   for (int c = 0; c < NC; c++) {
     dxs[c] = g.dxcf[q2 + c]; dxn[c] = g.dxcf[q2 + PX + c]; az[c] = g.azcc[q2 + c];
     kbc[c] = g.kb[q2 + c];
-    kgen = max(kgen, (int)g.knear[q2 + c]);   // level k itself must be clear; the bottom-face flux is carried
-    kzero = min(kzero, (int)g.ksolid[q2 + c] - 3);
   }
+  kgen = g.kgen2[q2]; kzero = g.kzero2[q2];   // pair-based: identical for all columns of this thread
   // ---- vertical register window: WT[c][m] = T(i0+c, j, k-3+m)
   size_t q3 = q2 + (size_t)n2 * g.Hz;  // level k = 1
   float WT[NC][7];
@@ -88,17 +89,18 @@ __global__ void __launch_bounds__(128) k_tracer_tendency_v2(DevGrid g, const Dev
   for (int c = 0; c < NC; c++) FzT[c] = 0.f;
   for (int k = 1; k <= Nz; k++, q3 += n2) {
     float oT[NC];
+    bool skip = false;
     if (k <= kzero) {
 #pragma unroll
       for (int c = 0; c < NC; c++) { oT[c] = 0.f; FzT[c] = 0.f; }
-    } else if (k <= kgen) {   // always taken at k = 1 (or kzero + 1), so the carried flux is valid on the fast levels
-      for (int c = 0; c < NC; c++) {
-        float ft;
-        const float o = tracer_cell_generic1(gp, u, v, w, T, i0 + c, j, k, &ft);
-#pragma unroll
-        for (int cc = 0; cc < NC; cc++) if (cc == c) { oT[cc] = o; FzT[cc] = ft; }
-      }
+    } else if (k <= kgen) {
+      // generic cells (bathymetry / a wall in the stencil) are computed by k_generic_list: nothing to do here
+      skip = true;
     } else {
+      if (k == kgen + 1 && kgen > 0) {   // first fast level: the flux through its bottom face was left by k_generic_list
+#pragma unroll
+        for (int c = 0; c < NC; c++) FzT[c] = carry[q2 + c];
+      }
       const float dz = g.dzc[k + g.Hz - 1];
       // ------------- x: faces i0 .. i0+NC from the row (i0-4 .. i0+NC+3)
       float rT[NC + 8];
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(128) k_tracer_tendency_v2(DevGrid g, const Dev
         FzT[c] = ftT;
       }
     }
-    stv<NC>(GT + q3, oT);
+    if (!skip) stv<NC>(GT + q3, oT);
     // ---- shift the vertical window and fetch level k+4
     {
       float a[NC];
@@ -165,7 +167,7 @@ void launch_tracer_tendency_v2(Handle* h) {
   const DevGrid& g = h->g;
   constexpr int NC = GB25_TRACER_NC;
   dim3 b(32 / NC, 128 * NC / 32), gr((g.Nx / NC + b.x - 1) / b.x, (g.Ny + b.y - 1) / b.y, 2);
-  k_tracer_tendency_v2<NC><<<gr, b, 0, h->stream>>>(g, h->g_dev, h->f.u, h->f.v, h->f.w, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3]);
+  k_tracer_tendency_v2<NC><<<gr, b, 0, h->stream>>>(g, h->g_dev, h->f.u, h->f.v, h->f.w, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3], h->carry[2], h->carry[3]);
   h->count_launch();
 }
 
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(128) k_gu_v2(DevGrid g, const DevGrid* __restr
                                                const float* __restrict__ v, const float* __restrict__ w,
                                                const float* __restrict__ p, const float* __restrict__ zeta,
                                                const float* __restrict__ dxU, const float* __restrict__ dyV,
-                                               float* __restrict__ G) {
+                                               float* __restrict__ G, const float* __restrict__ carry) {
   constexpr int NC = 2;
   const int i0 = NC * (blockIdx.x * blockDim.x + threadIdx.x) + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
@@ -262,13 +264,12 @@ __global__ void __launch_bounds__(128) k_gu_v2(DevGrid g, const DevGrid* __restr
   int kbc[NC], kgen = 0, kzero = GB25_BIG;
 #pragma unroll
   for (int c = 0; c < NC; c++) {
-    kzero = min(kzero, g.cond_diff ? (int)g.ksolid[q2 + c] - 3 : 0);
     m1[c] = g.dxfc[q2 + c];
     rV0[c] = g.azfc[q2 + c];
     fbar[c] = (g.fff[q2 + c] + g.fff[q2 + c + PX]) * 0.5f;
     kbc[c] = g.kb[q2 + c];
-    kgen = max(kgen, (int)g.knear[q2 + c]);   // level k itself must be clear; the bottom-face flux is carried
   }
+  kgen = g.kgen2[q2]; kzero = g.kzero2[q2];
 #pragma unroll
   for (int c = 0; c <= NC; c++) { mv[0][c] = g.dxcf[q2 + c - 1]; mv[1][c] = g.dxcf[q2 + c - 1 + PX]; }
 #pragma unroll
@@ -284,16 +285,13 @@ __global__ void __launch_bounds__(128) k_gu_v2(DevGrid g, const DevGrid* __restr
   float Wb[NC] = {0.f, 0.f};   // carried vertical flux through the bottom face (set by the generic path at k = 1)
   for (int k = 1; k <= Nz; k++, q3 += n2) {
     float out[NC];
+    bool skip = false;
     if (k <= kzero) {   // solid rock all around: u = v = 0, every flux masked, pressure difference conditional => G = 0
       out[0] = out[1] = 0.f; Wb[0] = Wb[1] = 0.f;
     } else if (k <= kgen) {
-      for (int c = 0; c < NC; c++) {
-        float wt;
-        const float o = momentum_G_call<0>(gp, u, v, w, p, i0 + c, j, k, &wt);
-#pragma unroll
-        for (int cc = 0; cc < NC; cc++) if (cc == c) { out[cc] = o; Wb[cc] = wt; }
-      }
+      skip = true;   // generic cells are computed by k_generic_list
     } else {
+      if (k == kgen + 1 && kgen > 0) { Wb[0] = carry[q2]; Wb[1] = carry[q2 + 1]; }
       const float dz = g.dzc[k + g.Hz - 1];
       // ---- rows of u (row j: cols i0-4 .. i0+5; rows j-3..j+3: cols i0, i0+1)
       float ur[10];
@@ -374,7 +372,7 @@ __global__ void __launch_bounds__(128) k_gu_v2(DevGrid g, const DevGrid* __restr
         out[c] = -(Hterm + Vterm + Bterm) - cor - dp;
       }
     }
-    *reinterpret_cast<float2*>(G + q3) = make_float2(out[0], out[1]);
+    if (!skip) *reinterpret_cast<float2*>(G + q3) = make_float2(out[0], out[1]);
     {
       const float2 a = ld2(u + q3 + (size_t)4 * n2);
 #pragma unroll
@@ -393,7 +391,7 @@ __global__ void __launch_bounds__(128) k_gv_v2(DevGrid g, const DevGrid* __restr
                                                const float* __restrict__ v, const float* __restrict__ w,
                                                const float* __restrict__ p, const float* __restrict__ zeta,
                                                const float* __restrict__ dxU, const float* __restrict__ dyV,
-                                               float* __restrict__ G) {
+                                               float* __restrict__ G, const float* __restrict__ carry) {
   constexpr int NC = 2;
   const int i0 = NC * (blockIdx.x * blockDim.x + threadIdx.x) + 1;
   const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
@@ -406,17 +404,16 @@ __global__ void __launch_bounds__(128) k_gv_v2(DevGrid g, const DevGrid* __restr
   int kbc[NC], kgen = 0, kzero = GB25_BIG;
 #pragma unroll
   for (int c = 0; c < NC; c++) {
-    kzero = min(kzero, g.cond_diff ? (int)g.ksolid[q2 + c] - 3 : 0);
     m1[c] = g.dycf[q2 + c];
     rV0[c] = g.azcf[q2 + c];
     fbar[c] = (g.fff[q2 + c] + g.fff[q2 + c + 1]) * 0.5f;
     kbc[c] = g.kb[q2 + c];
-    kgen = max(kgen, (int)g.knear[q2 + c]);   // level k itself must be clear; the bottom-face flux is carried
 #pragma unroll
     for (int m = 0; m < 4; m++) azw[m][c] = g.azcc[q2 + c + (m - 2) * PX];
   }
 #pragma unroll
   for (int c = 0; c <= NC; c++) { mu[0][c] = g.dyfc[q2 + c - PX]; mu[1][c] = g.dyfc[q2 + c]; }
+  kgen = g.kgen2[q2]; kzero = g.kzero2[q2];
   // ---- vertical register window of v
   size_t q3 = q2 + (size_t)n2 * g.Hz;
   float WV[NC][7];
@@ -428,16 +425,13 @@ __global__ void __launch_bounds__(128) k_gv_v2(DevGrid g, const DevGrid* __restr
   float Wb[NC] = {0.f, 0.f};
   for (int k = 1; k <= Nz; k++, q3 += n2) {
     float out[NC];
+    bool skip = false;
     if (k <= kzero) {
       out[0] = out[1] = 0.f; Wb[0] = Wb[1] = 0.f;
     } else if (k <= kgen) {
-      for (int c = 0; c < NC; c++) {
-        float wt;
-        const float o = momentum_G_call<1>(gp, v, u, w, p, i0 + c, j, k, &wt);
-#pragma unroll
-        for (int cc = 0; cc < NC; cc++) if (cc == c) { out[cc] = o; Wb[cc] = wt; }
-      }
+      skip = true;   // generic cells are computed by k_generic_list
     } else {
+      if (k == kgen + 1 && kgen > 0) { Wb[0] = carry[q2]; Wb[1] = carry[q2 + 1]; }
       const float dz = g.dzc[k + g.Hz - 1];
       // ---- v: row j cols i0-4 .. i0+5; rows j-3..j+3 cols i0, i0+1
       float vr[10];
@@ -516,7 +510,7 @@ __global__ void __launch_bounds__(128) k_gv_v2(DevGrid g, const DevGrid* __restr
         out[c] = -(Hterm + Vterm + Bterm) - cor - dp;
       }
     }
-    *reinterpret_cast<float2*>(G + q3) = make_float2(out[0], out[1]);
+    if (!skip) *reinterpret_cast<float2*>(G + q3) = make_float2(out[0], out[1]);
     {
       const float2 a = ld2(v + q3 + (size_t)4 * n2);
 #pragma unroll
@@ -532,6 +526,48 @@ __global__ void __launch_bounds__(128) k_gv_v2(DevGrid g, const DevGrid* __restr
 void launch_momentum_tendency_v2(Handle* h) {
   const DevGrid& g = h->g;
   dim3 b(16, 8), gr((g.Nx / 2 + b.x - 1) / b.x, (g.Ny + b.y - 1) / b.y);
-  k_gu_v2<<<gr, b, 0, h->stream>>>(g, h->g_dev, h->f.u, h->f.v, h->f.w, h->f.p, h->zeta, h->dxU, h->dyV, h->f.gn[0]); h->count_launch();
-  k_gv_v2<<<gr, b, 0, h->stream>>>(g, h->g_dev, h->f.u, h->f.v, h->f.w, h->f.p, h->zeta, h->dxU, h->dyV, h->f.gn[1]); h->count_launch();
+  k_gu_v2<<<gr, b, 0, h->stream>>>(g, h->g_dev, h->f.u, h->f.v, h->f.w, h->f.p, h->zeta, h->dxU, h->dyV, h->f.gn[0], h->carry[0]); h->count_launch();
+  k_gv_v2<<<gr, b, 0, h->stream>>>(g, h->g_dev, h->f.u, h->f.v, h->f.w, h->f.p, h->zeta, h->dxU, h->dyV, h->f.gn[1], h->carry[1]); h->count_launch();
+}
+
+// =====================================================================================
+// Generic cells (bathymetry or a wall somewhere in the stencil: ~1.5 % of the cells of the 1/4-degree tripolar
+// workload) handled as a flat list, one thread per cell, all four tendencies at once.  Inside the blocked kernels
+// these cells stalled whole warps / CTAs (a generic cell costs ~3x a fast one and reads global memory); here they
+// run at full occupancy.  The topmost generic cell of a column leaves the vertical fluxes through its top face in
+// the 2-D carry arrays, where the fast kernels pick them up.
+// =====================================================================================
+__global__ void __launch_bounds__(128) k_generic_list(DevGrid g, const DevGrid* __restrict__ gp, const float* __restrict__ u,
+                                                      const float* __restrict__ v, const float* __restrict__ w,
+                                                      const float* __restrict__ p, const float* __restrict__ T,
+                                                      const float* __restrict__ S, float* __restrict__ Gu, float* __restrict__ Gv,
+                                                      float* __restrict__ GT, float* __restrict__ GS, float* __restrict__ cu,
+                                                      float* __restrict__ cv, float* __restrict__ cT, float* __restrict__ cS,
+                                                      int do_mom, int do_trc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.nglist) return;
+  const int q3 = g.glist[idx];
+  const int K = q3 / g.n2, r = q3 - K * g.n2, J = r / g.PX, I = r - J * g.PX;
+  const int i = I - g.Hx + 1, j = J - g.Hy + 1, k = K - g.Hz + 1;
+  const bool top = (k == (int)g.kgen2[r]) && k < g.Nz;
+  if (do_mom) {
+    float wu, wv;
+    Gu[q3] = momentum_G<0>(g, u, v, w, p, i, j, k, &wu);
+    Gv[q3] = momentum_G<1>(g, v, u, w, p, i, j, k, &wv);
+    if (top) { cu[r] = wu; cv[r] = wv; }
+  }
+  if (do_trc) {
+    float fT, fS;
+    GT[q3] = tracer_cell_generic1(gp, u, v, w, T, i, j, k, &fT);
+    GS[q3] = tracer_cell_generic1(gp, u, v, w, S, i, j, k, &fS);
+    if (top) { cT[r] = fT; cS[r] = fS; }
+  }
+}
+void launch_generic_list(Handle* h, bool momentum, bool tracers) {
+  const DevGrid& g = h->g;
+  if (g.nglist == 0) return;
+  k_generic_list<<<(g.nglist + 127) / 128, 128, 0, h->stream>>>(g, h->g_dev, h->f.u, h->f.v, h->f.w, h->f.p, h->f.T, h->f.S,
+                                                              h->f.gn[0], h->f.gn[1], h->f.gn[2], h->f.gn[3], h->carry[0],
+                                                              h->carry[1], h->carry[2], h->carry[3], momentum ? 1 : 0, tracers ? 1 : 0);
+  h->count_launch();
 }
