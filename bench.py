@@ -39,8 +39,15 @@ WORKLOADS = {
 }
 ALGORITHMIC_BYTES_PER_CELL_STEP = 104     # 26 Float32 words of compulsory 3-D traffic
 # algorithmic bytes per cell of one launch of each tendency kernel (DESIGN.md "kernels")
-KERNEL_BYTES_PER_CELL = {"momentum_tendencies": 2 * (4 + 1) * 4,   # two launches: read u,v,w,p, write G
-                         "tracer_tendencies": (5 + 2) * 4}         # read u,v,w,T,S, write GT,GS
+# ("kernel:<name>" entries are single-launch CUDA-event timers of libgb25cuda)
+KERNEL_BYTES_PER_CELL = {"kernel:k_tracer_tendency_v2": (5 + 2) * 4,   # one launch, both tracers: read u,v,w,T,S, write GT,GS
+                         "kernel:k_gu_tma": (4 + 1) * 4,                # read u,v,w,p, write Gu
+                         "kernel:k_gv_tma": (4 + 1) * 4,
+                         "kernel:k_ab2_fused": 16 * 4,                  # read 4 fields + 8 G, write 4 fields
+                         "momentum_tendencies": 2 * (4 + 1) * 4, "tracer_tendencies": (5 + 2) * 4}
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` captures under
+# profiles/ (tripolar 1440x600x50 workload); None = not captured for this kernel version
+NCU_TRAFFIC_BYTES = {"kernel:k_tracer_tendency_v2": None, "kernel:k_gu_tma": None, "kernel:k_gv_tma": None}
 
 
 def measured_peaks():
@@ -53,7 +60,7 @@ def measured_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
@@ -64,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)],
+                                          "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -75,7 +82,9 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples whose timestamp falls inside [t0, t1] (the timed region; wall-clock seconds)."""
+        import datetime
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -89,6 +98,10 @@ class ClockSampler:
             if len(f) < 8:
                 continue
             try:
+                if t0 is not None:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if ts < t0 - 0.05 or ts > t1 + 0.05:
+                        continue
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
@@ -173,7 +186,7 @@ def cpu_baseline_sample(workload, budget_s=20.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tripolar_quarter_degree", choices=sorted(WORKLOADS))
@@ -228,17 +241,20 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)      # let nvidia-smi come up so that the timed region is covered by samples
     l0 = model.handle.launch_count()
     model.handle.call("gb25_enable_stage_timers", 1)
     barrier()
+    wall0 = time.time()
     M.loop(model, args.steps)
     model.synchronize()
+    wall1 = time.time()
     secs = model.handle.last_loop_seconds()
     barrier()
     stages = model.handle.stage_times()
     model.handle.call("gb25_enable_stage_timers", 0)
     launches = model.handle.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     if dist is not None:
         t = torch.tensor([secs], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -287,20 +303,26 @@ def main():
         return
     hbm, peak_src = measured_peaks()
     # dominant kernel = the stage with the largest share of the step
+    kernels = {k: v for k, v in stages.items() if k.startswith("kernel:")}
+    stages = {k: v for k, v in stages.items() if not k.startswith("kernel:")}
     tot_ms = sum(ms for ms, _ in stages.values()) or 1.0
-    dom = max((k for k in stages if k in KERNEL_BYTES_PER_CELL), key=lambda k: stages[k][0], default=None)
+    pool = kernels if any(k in KERNEL_BYTES_PER_CELL for k in kernels) else stages
+    dom = max((k for k in pool if k in KERNEL_BYTES_PER_CELL), key=lambda k: pool[k][0], default=None)
     roofline = None
     if dom:
-        ms, calls = stages[dom]
+        ms, calls = pool[dom]
         per_call_s = ms * 1e-3 / max(calls, 1)
         achieved = KERNEL_BYTES_PER_CELL[dom] * cells_per_rank / per_call_s / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                    "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / hbm,
+                    "traffic": (NCU_TRAFFIC_BYTES.get(dom) if args.workload == "tripolar_quarter_degree" and world == 1 else None),
+                    "algorithmic_bytes_per_launch": KERNEL_BYTES_PER_CELL[dom] * cells_per_rank, "peak_source": peak_src,
                     "avg_launch_ms": per_call_s * 1e3, "share_of_step": ms / tot_ms,
                     "whole_step": {"algorithmic_bytes_per_cell_step": ALGORITHMIC_BYTES_PER_CELL_STEP,
                                    "achieved": ALGORITHMIC_BYTES_PER_CELL_STEP * value / world / 1e9,
                                    "frac": ALGORITHMIC_BYTES_PER_CELL_STEP * value / world / 1e9 / hbm},
-                    "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()}}
+                    "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
+                    "kernel_ms_per_launch": {k[7:]: v[0] / max(v[1], 1) for k, v in kernels.items()}}
     line = {"metric": "cell_steps_per_s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",

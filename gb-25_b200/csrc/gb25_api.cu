@@ -42,22 +42,7 @@ static int check_async(Handle* h, const char* what) {
   return GB25_OK;
 }
 
-// ------------------------------------------------------------------ stage timers
-struct StageScope {
-  Handle* h; StageTimer* t = nullptr; size_t slot = 0;
-  StageScope(Handle* h_, const char* name) : h(h_) {
-    if (!h->timers_on) return;
-    for (auto& s : h->timers) if (s.name == name || !strcmp(s.name, name)) { t = &s; break; }
-    if (!t) { h->timers.push_back(StageTimer{name}); t = &h->timers.back(); }
-    if (t->used == t->ev.size()) {
-      cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-      t->ev.push_back({a, b});
-    }
-    slot = t->used++;
-    cudaEventRecord(t->ev[slot].first, h->stream);
-  }
-  ~StageScope() { if (t) cudaEventRecord(t->ev[slot].second, h->stream); }
-};
+// ------------------------------------------------------------------ stage timers (StageScope: gb25_internal.h)
 static void drain_timers(Handle* h) {
   for (auto& s : h->timers) {
     for (size_t q = 0; q < s.used; q++) {

@@ -76,6 +76,25 @@ struct gb25_handle {
 };
 typedef gb25_handle Handle;
 
+// RAII CUDA-event timer on the handle's stream (active only while gb25_enable_stage_timers is on).
+// Names starting with "kernel:" time a single kernel launch.
+#include <cstring>
+struct StageScope {
+  Handle* h; StageTimer* t = nullptr; size_t slot = 0;
+  StageScope(Handle* h_, const char* name) : h(h_) {
+    if (!h->timers_on) return;
+    for (auto& s : h->timers) if (s.name == name || !strcmp(s.name, name)) { t = &s; break; }
+    if (!t) { h->timers.push_back(StageTimer{name}); t = &h->timers.back(); }
+    if (t->used == t->ev.size()) {
+      cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+      t->ev.push_back({a, b});
+    }
+    slot = t->used++;
+    cudaEventRecord(t->ev[slot].first, h->stream);
+  }
+  ~StageScope() { if (t) cudaEventRecord(t->ev[slot].second, h->stream); }
+};
+
 // stage launchers (gb25_kernels.cu)
 void launch_fill_halo(Handle* h, const HaloSpec* specs, int n, bool three_d);
 void launch_halo_south_north(Handle* h, const HaloSpec* specs, int n, bool three_d, int mode_s, int mode_n);

@@ -484,6 +484,7 @@ __global__ void k_correct_fused(DevGrid g, DevFields f, const float* __restrict_
 void launch_ab2_fused(Handle* h, float dt, float chi) {
   const DevGrid& g = h->g;
   dim3 b(128), gr((g.Nx + 127) / 128, g.Ny);
+  StageScope ts(h, "kernel:k_ab2_fused");
   k_ab2_fused<<<gr, b, 0, h->stream>>>(g, h->f, h->us2, h->vs2, dt, chi); h->count_launch();
 }
 void launch_correct_fused(Handle* h) {

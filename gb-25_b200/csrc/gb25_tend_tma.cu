@@ -427,8 +427,10 @@ void launch_momentum_tendency_tma(Handle* h) {
   TmaState* t = tma_state(h);
   const DevGrid& g = h->g;
   dim3 b(TMA_TX, TMA_TY + 1), gr((g.Nx + TMA_TX - 1) / TMA_TX, (g.Ny + TMA_TY - 1) / TMA_TY);
-  k_gu_tma<<<gr, b, TMA_NST * GU_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gu, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[0], h->carry[0]);
+  { StageScope ts(h, "kernel:k_gu_tma");
+  k_gu_tma<<<gr, b, TMA_NST * GU_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gu, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[0], h->carry[0]); }
   h->count_launch();
-  k_gv_tma<<<gr, b, TMA_NST * GV_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gv, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[1], h->carry[1]);
+  { StageScope ts(h, "kernel:k_gv_tma");
+  k_gv_tma<<<gr, b, TMA_NST * GV_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gv, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[1], h->carry[1]); }
   h->count_launch();
 }

@@ -167,6 +167,7 @@ void launch_tracer_tendency_v2(Handle* h) {
   const DevGrid& g = h->g;
   constexpr int NC = GB25_TRACER_NC;
   dim3 b(32 / NC, 128 * NC / 32), gr((g.Nx / NC + b.x - 1) / b.x, (g.Ny + b.y - 1) / b.y, 2);
+  StageScope ts(h, "kernel:k_tracer_tendency_v2");
   k_tracer_tendency_v2<NC><<<gr, b, 0, h->stream>>>(g, h->g_dev, h->f.u, h->f.v, h->f.w, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3], h->carry[2], h->carry[3]);
   h->count_launch();
 }
@@ -217,6 +218,7 @@ void launch_aux_columns(Handle* h) {
   const DevGrid& g = h->g;
   const int nx = g.Nx + 2 * g.Hx - 2, ny = g.Ny + 2 * g.Hy - 2;
   dim3 b(128), gr((nx + 127) / 128, ny);
+  StageScope ts(h, "kernel:k_aux_columns");
   k_aux_columns<<<gr, b, 0, h->stream>>>(g, h->f.u, h->f.v, h->f.w, h->zeta, h->dxU, h->dyV);
   h->count_launch();
 }
@@ -566,6 +568,7 @@ __global__ void __launch_bounds__(128) k_generic_list(DevGrid g, const DevGrid* 
 void launch_generic_list(Handle* h, bool momentum, bool tracers) {
   const DevGrid& g = h->g;
   if (g.nglist == 0) return;
+  StageScope ts(h, "kernel:k_generic_list");
   k_generic_list<<<(g.nglist + 127) / 128, 128, 0, h->stream>>>(g, h->g_dev, h->f.u, h->f.v, h->f.w, h->f.p, h->f.T, h->f.S,
                                                               h->f.gn[0], h->f.gn[1], h->f.gn[2], h->f.gn[3], h->carry[0],
                                                               h->carry[1], h->carry[2], h->carry[3], momentum ? 1 : 0, tracers ? 1 : 0);

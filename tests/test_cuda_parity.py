@@ -213,3 +213,19 @@ def test_fused_step_path_equals_operator_path(oracle_mod, monkeypatch, grid_type
         for _ in range(4):
             M.time_step(m)
     assert M.compare_states(rm_f, rm_o, include_halos=True, rtol=2e-5, atol=0.0, verbose=False, elementwise=2e-5)
+
+
+@pytest.mark.parametrize("grid_type,Nx,Ny,Nz", GRIDS)
+def test_tma_kernels_equal_blocked_kernels(oracle_mod, monkeypatch, grid_type, Nx, Ny, Nz):
+    """The TMA-staged momentum kernels evaluate the same expressions as the register-blocked ones (GB25_TMA=0);
+    only the compiler's FMA contraction differs between the two instruction streams, so the model states agree
+    to a few ulp (two orders of magnitude inside the reference tolerance)."""
+    rm_t, vm = make_models(grid_type, Nx, Ny, Nz, 60.0, oracle_mod)
+    monkeypatch.setenv("GB25_TMA", "0")
+    rm_b, _ = make_models(grid_type, Nx, Ny, Nz, 60.0, oracle_mod)
+    monkeypatch.delenv("GB25_TMA")
+    for m in (rm_t, rm_b):
+        M.first_time_step(m)
+        for _ in range(4):
+            M.time_step(m)
+    assert M.compare_states(rm_t, rm_b, include_halos=True, rtol=3e-6, atol=0.0, verbose=False, elementwise=1e-5)
