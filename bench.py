@@ -47,7 +47,8 @@ KERNEL_BYTES_PER_CELL = {"kernel:k_tracer_tendency_v2": (5 + 2) * 4,   # one lau
                          "momentum_tendencies": 2 * (4 + 1) * 4, "tracer_tendencies": (5 + 2) * 4}
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` captures under
 # profiles/ (tripolar 1440x600x50 workload); None = not captured for this kernel version
-NCU_TRAFFIC_BYTES = {"kernel:k_tracer_tendency_v2": None, "kernel:k_gu_tma": None, "kernel:k_gv_tma": None}
+NCU_TRAFFIC_BYTES = {"kernel:k_tracer_tendency_v2": 1459761000 + 330897408,   # profiles/ncu_r1_v3_top_kernels.md
+                     "kernel:k_gu_tma": 1327310000 + 169361408, "kernel:k_gv_tma": 1404815000 + 168233728}
 
 
 def measured_peaks():
