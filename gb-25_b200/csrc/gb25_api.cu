@@ -219,6 +219,10 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     g_create_error = "gb25_create: unsupported sizes (need Nx,Ny >= 8, halo >= 4, 1 <= nsubsteps <= 256)";
     return GB25_ERR_INVALID;
   }
+  if (cfg->closure < 0 || cfg->closure > 2 || (cfg->closure && (cfg->kappa < 0.f || cfg->nu < 0.f))) {
+    g_create_error = "gb25_create: closure must be 0 (nothing), 1 (explicit) or 2 (vertically implicit) with kappa, nu >= 0";
+    return GB25_ERR_INVALID;
+  }
   if (cfg->topo_y == GB25_TOPO_FOLD && (cfg->Nx % 2)) { g_create_error = "gb25_create: tripolar fold needs even Nx"; return GB25_ERR_INVALID; }
   if (!grid->dx_cc || !grid->z_f || !grid->z_c || !grid->dz_c || !grid->dz_f || !grid->avg_weights || !grid->f_ff) {
     g_create_error = "gb25_create: missing grid array"; return GB25_ERR_INVALID;
@@ -393,6 +397,7 @@ static void stage_aux(Handle* h) {
 static void stage_tend(Handle* h) {
   { StageScope t(h, "momentum_tendencies"); launch_momentum_tendency(h); }
   { StageScope t(h, "tracer_tendencies"); launch_tracer_tendency(h); }
+  if (h->cfg.closure == 1) { StageScope t(h, "vertical_diffusion"); launch_vdiff_explicit(h); }
 }
 static void stage_update_state(Handle* h) {
   stage_mask(h);
@@ -403,6 +408,7 @@ static void stage_update_state(Handle* h) {
 static void stage_ab2(Handle* h, float dt, float chi) {
   DevFields& f = h->f;
   { StageScope t(h, "ab2_step_fields"); launch_ab2_columns(h, dt, chi); }
+  if (h->cfg.closure == 2) { StageScope t(h, "vertical_diffusion"); launch_implicit_columns(h, dt, false); }
   {
     StageScope t(h, "split_explicit_free_surface");
     HaloSpec sg[2] = {{f.gU, 1, 0, 0, -1.f}, {f.gV, 0, 1, 0, -1.f}};
@@ -424,6 +430,7 @@ static void stage_initialize(Handle* h) {
 static void one_time_step_fused(Handle* h, float dt, float chi) {
   DevFields& f = h->f;
   { StageScope t(h, "ab2_step_fields"); launch_ab2_fused(h, dt, chi); }
+  if (h->cfg.closure == 2) { StageScope t(h, "vertical_diffusion"); launch_implicit_columns(h, dt, true); }
   {
     StageScope t(h, "split_explicit_free_surface");
     HaloSpec sg[2] = {{f.gU, 1, 0, 0, -1.f}, {f.gV, 0, 1, 0, -1.f}};

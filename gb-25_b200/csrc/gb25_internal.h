@@ -125,4 +125,6 @@ void launch_correct_cache(Handle* h);
 void launch_barotropic_mode(Handle* h);
 void launch_ab2_fused(Handle* h, float dt, float chi);
 void launch_correct_fused(Handle* h);
+void launch_vdiff_explicit(Handle* h);
+void launch_implicit_columns(Handle* h, float dt, bool with_sums);
 void launch_barotropic_substeps(Handle* h, float dt);

@@ -492,3 +492,96 @@ void launch_correct_fused(Handle* h) {
   dim3 b(128), gr((g.Nx + 127) / 128, g.Ny);
   k_correct_fused<<<gr, b, 0, h->stream>>>(g, h->f, h->us2, h->vs2); h->count_launch();
 }
+
+// =====================================================================================
+// Vertical diffusion (row A13): VerticalScalarDiffusivity(kappa, nu), constant coefficients.
+// A face is "open" when it is not a peripheral node: 2 <= k <= Nz and every adjacent cell is fluid.
+// =====================================================================================
+__device__ __forceinline__ int vdiff_kbm(const DevGrid& g, int q2, int j, int fld) {
+  // highest solid level among the columns adjacent to the node (u: i-1,i ; v: j-1,j ; T,S: own); walls -> BIG
+  const int kb0 = g.kb[q2];
+  if (fld == 0) return max(kb0, (int)g.kb[q2 - 1]);
+  if (fld == 1) return (y_outside(g, j) || y_outside(g, j - 1)) ? GB25_BIG : max(kb0, (int)g.kb[q2 - g.PX]);
+  return kb0;
+}
+__global__ void k_vdiff_explicit(DevGrid g, DevFields f, float kappa, float nu) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1, k = blockIdx.z + 1;
+  if (i > g.Nx) return;
+  const int q2 = id2(g, i, j), n2 = g.n2;
+  const size_t q3 = q2 + (size_t)n2 * (k + g.Hz - 1);
+  const float dzc = g.dzc[k + g.Hz - 1], dzt = g.dzf[k + 1 + g.Hz - 1], dzb = g.dzf[k + g.Hz - 1];
+  float* fld[4] = {f.u, f.v, f.T, f.S};
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int kbm = vdiff_kbm(g, q2, j, q);
+    const float K = q < 2 ? nu : kappa;
+    const float* c = fld[q] + q3;
+    const bool open_t = (k + 1 <= g.Nz) && (k > kbm), open_b = (k >= 2) && (k - 1 > kbm);
+    const float qt = open_t ? K * (c[n2] - c[0]) / dzt : 0.f;
+    const float qb = open_b ? K * (c[0] - c[-n2]) / dzb : 0.f;
+    f.gn[q][q3] = f.gn[q][q3] + (qt - qb) / dzc;
+  }
+}
+void launch_vdiff_explicit(Handle* h) {
+  const DevGrid& g = h->g;
+  dim3 b(128), gr((g.Nx + 127) / 128, g.Ny, g.Nz);
+  k_vdiff_explicit<<<gr, b, 0, h->stream>>>(g, h->f, h->cfg.kappa, h->cfg.nu); h->count_launch();
+}
+// implicit: (I - dt d_z K d_z) c = c*, Thomas algorithm per column (Oceananigans' batched tridiagonal solver);
+// the elimination factors t[k] go through a 3-D scratch array (the zeta scratch, rebuilt later in the step)
+__global__ void k_implicit_columns(DevGrid g, DevFields f, float* __restrict__ scratch, float dt, float kappa, float nu,
+                                   float* __restrict__ us2, float* __restrict__ vs2, int with_sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.Nx) return;
+  const int q2 = id2(g, i, j), n2 = g.n2, Nz = g.Nz;
+  const size_t q1 = q2 + (size_t)n2 * g.Hz;   // level 1
+  float* fld[4] = {f.u, f.v, f.T, f.S};
+#pragma unroll 1
+  for (int q = 0; q < 4; q++) {
+    const int kbm = vdiff_kbm(g, q2, j, q);
+    const float K = q < 2 ? nu : kappa;
+    float* c = fld[q] + q1;     // c[(k-1)*n2]
+    float* t = scratch + q1;
+    auto upper = [&](int k) -> float {   // face k+1
+      if (k > Nz - 1) return 0.f;
+      return (k > kbm) ? -dt * K / (g.dzc[k + g.Hz - 1] * g.dzf[k + 1 + g.Hz - 1]) : 0.f;
+    };
+    auto lower = [&](int kp) -> float {  // face k = kp+1
+      if (kp < 1) return 0.f;
+      const int k = kp + 1;
+      return (k - 1 > kbm) ? -dt * K / (g.dzc[k + g.Hz - 1] * g.dzf[k + g.Hz - 1]) : 0.f;
+    };
+    float beta = 1.f - upper(1) - lower(0);
+    float prev = c[0] / beta;
+    c[0] = prev;
+    for (int k = 2; k <= Nz; k++) {
+      const float lo = lower(k - 1);
+      const float tk = upper(k - 1) / beta;
+      t[(size_t)(k - 1) * n2] = tk;
+      beta = (1.f - upper(k) - lo) - lo * tk;
+      prev = (c[(size_t)(k - 1) * n2] - lo * prev) / beta;
+      c[(size_t)(k - 1) * n2] = prev;
+    }
+    for (int k = Nz - 1; k >= 1; k--) {
+      prev = c[(size_t)(k - 1) * n2] - t[(size_t)k * n2] * prev;
+      c[(size_t)(k - 1) * n2] = prev;
+    }
+  }
+  if (with_sums) {   // the corrector's column sums must see the diffused velocities
+    float bu = 0.f, bv = 0.f;
+    size_t q3 = q1;
+    for (int k = 1; k <= Nz; k++, q3 += n2) {
+      const float dz = g.dzc[k + g.Hz - 1];
+      const float wu = dz * f.u[q3], wv = dz * f.v[q3];
+      bu = (k == 1) ? wu : bu + wu;
+      bv = (k == 1) ? wv : bv + wv;
+    }
+    us2[q2] = bu; vs2[q2] = bv;
+  }
+}
+void launch_implicit_columns(Handle* h, float dt, bool with_sums) {
+  const DevGrid& g = h->g;
+  dim3 b(128), gr((g.Nx + 127) / 128, g.Ny);
+  k_implicit_columns<<<gr, b, 0, h->stream>>>(g, h->f, h->zeta, dt, h->cfg.kappa, h->cfg.nu, h->us2, h->vs2, with_sums ? 1 : 0);
+  h->count_launch();
+}

@@ -55,7 +55,8 @@ class gb25_config(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("Nx", "Ny", "Nz", "Hx", "Hy", "Hz", "topo_y", "immersed", "nsubsteps",
                                        "coriolis_scheme", "fold_variant", "south_inactive", "cond_diff", "eos_r0")] + \
                [(n, C.c_float) for n in ("g", "rho0", "chi", "dtau_frac", "weno_eps")] + \
-               [(n, C.c_int) for n in ("Rx", "Ry", "rx", "ry", "device")]
+               [(n, C.c_int) for n in ("Rx", "Ry", "rx", "ry", "device", "closure")] + \
+               [(n, C.c_float) for n in ("kappa", "nu")]
 
 
 _GRID_PTRS = ("dx_cc", "dx_fc", "dx_cf", "dx_ff", "dy_cc", "dy_fc", "dy_cf", "dy_ff",
@@ -129,6 +130,7 @@ class Handle:
         cfg.g, cfg.rho0, cfg.chi, cfg.dtau_frac, cfg.weno_eps = physics.g, physics.rho0, physics.chi, dtau_frac, physics.weno_eps
         cfg.Rx, cfg.Ry, cfg.rx, cfg.ry = partition
         cfg.device = device
+        cfg.closure, cfg.kappa, cfg.nu = physics.closure, physics.kappa, physics.nu
         g = gb25_grid()
         arrays = dict(grid.metrics)
         arrays.update(grid.z)

@@ -62,6 +62,11 @@ typedef struct {
    * sharding/sharded_baroclinic_instability_simulation_run.jl:65-72; rank = rx + Rx*ry */
   int Rx, Ry, rx, ry;
   int device;              /* CUDA device ordinal to use (-1: current device)                      */
+  /* closure: 0 = nothing (reference default, src/baroclinic_instability_model.jl:29),
+   * 1 = VerticalScalarDiffusivity(kappa, nu) explicit, 2 = VerticallyImplicitTimeDiscretization (the commented
+   * alternative at src/baroclinic_instability_model.jl:31 with kappa = 1e-5, nu = 1e-4)                           */
+  int closure;
+  float kappa, nu;
 } gb25_config;
 
 /* Grid products, all host pointers.  2-D arrays have (Nx+2Hx) x (Ny+2Hy+1) elements, x fastest;

@@ -46,7 +46,8 @@ struct OConfig {
   int cond_diff;        // U15: immersed-aware (conditional) differences in zeta and grad p
   int eos_r0;           // U8: include r0(z) in rho'
   int beta_form;        // D1: 0 = expanded smoothness indicators (recalled reference form), 1 = sum of squares
-  double g, rho0, chi, dtau_frac, weno_eps;
+  int closure;          // A13: 0 = nothing, 1 = VerticalScalarDiffusivity explicit, 2 = vertically implicit
+  double g, rho0, chi, dtau_frac, weno_eps, kappa, nu;
 };
 }
 
@@ -603,10 +604,58 @@ struct Oracle {
           at(F_GNV, i, j, k) = gv(i, j, k);
         }
   }
+  // ------------------------------------------------- vertical diffusion (row A13)
+  // VerticalScalarDiffusivity(kappa, nu), constant coefficients.  Explicit: G += (1/V) delta_z(Az K d_z c) with zero
+  // flux through peripheral faces (walls, bathymetry).  Implicit: after the AB2 update solve, column by column,
+  // (I - dt d_z K d_z) c = c* with the Thomas algorithm of Oceananigans' batched tridiagonal solver.
+  void vertical_diffusion_explicit(int fc, int fg, Loc l, FT K) {
+    const Loc lf{l.x, l.y, 1};
+#pragma omp parallel for collapse(2)
+    for (int k = 1; k <= Nz; k++)
+      for (int j = 1; j <= Ny; j++)
+        for (int i = 1; i <= Nx; i++) {
+          FT qt = peripheral(lf, i, j, k + 1) ? (FT)0 : K * (at(fc, i, j, k + 1) - at(fc, i, j, k)) / Dzf(k + 1);
+          FT qb = peripheral(lf, i, j, k) ? (FT)0 : K * (at(fc, i, j, k) - at(fc, i, j, k - 1)) / Dzf(k);
+          at(fg, i, j, k) = at(fg, i, j, k) + (qt - qb) / Dzc(k);
+        }
+  }
+  void implicit_vertical_diffusion(int fc, Loc l, FT K, FT dt) {
+    const Loc lf{l.x, l.y, 1};
+#pragma omp parallel for
+    for (int j = 1; j <= Ny; j++) {
+      std::vector<FT> t(Nz + 2);
+      for (int i = 1; i <= Nx; i++) {
+        auto upper = [&](int k) -> FT {   // couples k and k+1 through face k+1
+          if (k > Nz - 1) return 0;
+          return peripheral(lf, i, j, k + 1) ? (FT)0 : -dt * K / (Dzc(k) * Dzf(k + 1));
+        };
+        auto lower = [&](int kp) -> FT {  // kp = k-1: couples k and k-1 through face k
+          if (kp < 1) return 0;
+          int k = kp + 1;
+          return peripheral(lf, i, j, k) ? (FT)0 : -dt * K / (Dzc(k) * Dzf(k));
+        };
+        auto diag = [&](int k) -> FT { return (FT)1 - upper(k) - lower(k - 1); };
+        FT beta = diag(1);
+        at(fc, i, j, 1) = at(fc, i, j, 1) / beta;
+        for (int k = 2; k <= Nz; k++) {
+          t[k] = upper(k - 1) / beta;
+          beta = diag(k) - lower(k - 1) * t[k];
+          at(fc, i, j, k) = (at(fc, i, j, k) - lower(k - 1) * at(fc, i, j, k - 1)) / beta;
+        }
+        for (int k = Nz - 1; k >= 1; k--) at(fc, i, j, k) -= t[k + 1] * at(fc, i, j, k + 1);
+      }
+    }
+  }
   void compute_tendencies() {
     momentum_tendency();
     tracer_tendency(F_T, F_GNT);
     tracer_tendency(F_S, F_GNS);
+    if (c.closure == 1) {
+      vertical_diffusion_explicit(F_U, F_GNU, {1, 0, 0}, (FT)c.nu);
+      vertical_diffusion_explicit(F_V, F_GNV, {0, 1, 0}, (FT)c.nu);
+      vertical_diffusion_explicit(F_T, F_GNT, {0, 0, 0}, (FT)c.kappa);
+      vertical_diffusion_explicit(F_S, F_GNS, {0, 0, 0}, (FT)c.kappa);
+    }
   }
   void compute_auxiliaries() { compute_w(); compute_p(); }
   void update_state() {
@@ -715,6 +764,12 @@ struct Oracle {
   void ab2_step(FT dt, FT chi) {
     free_surface_tendency(chi);
     ab2_fields(dt, chi);
+    if (c.closure == 2) {
+      implicit_vertical_diffusion(F_U, {1, 0, 0}, (FT)c.nu, dt);
+      implicit_vertical_diffusion(F_V, {0, 1, 0}, (FT)c.nu, dt);
+      implicit_vertical_diffusion(F_T, {0, 0, 0}, (FT)c.kappa, dt);
+      implicit_vertical_diffusion(F_S, {0, 0, 0}, (FT)c.kappa, dt);
+    }
     step_free_surface(dt);
   }
   // ------------------------------------------------- corrector + cache (rows A11, A12)

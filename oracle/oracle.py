@@ -29,8 +29,8 @@ LIB_PATH = os.path.join(_HERE, "libgb25oracle.so")
 
 class OConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("Nx", "Ny", "Nz", "Hx", "Hy", "Hz", "topo_y", "immersed", "nsub",
-                                       "coriolis_scheme", "fold_variant", "south_inactive", "cond_diff", "eos_r0", "beta_form")] + \
-               [(n, C.c_double) for n in ("g", "rho0", "chi", "dtau_frac", "weno_eps")]
+                                       "coriolis_scheme", "fold_variant", "south_inactive", "cond_diff", "eos_r0", "beta_form", "closure")] + \
+               [(n, C.c_double) for n in ("g", "rho0", "chi", "dtau_frac", "weno_eps", "kappa", "nu")]
 
 
 _lib = None
@@ -122,9 +122,10 @@ class OracleModel(ModelBase):
         self.dtau_frac, self.weights = averaging_weights(self.physics.substeps)
         p = self.physics
         cfg = OConfig(grid.Nx, grid.Ny, grid.Nz, grid.Hx, grid.Hy, grid.Hz, grid.topo_y, 1 if grid.immersed else 0,
-                      len(self.weights), p.coriolis_scheme, p.fold_variant, p.south_inactive, p.cond_diff, p.eos_r0, getattr(p, "oracle_beta_form", 0),
+                      len(self.weights), p.coriolis_scheme, p.fold_variant, p.south_inactive, p.cond_diff, p.eos_r0, getattr(p, "oracle_beta_form", 0), p.closure,
                       float(np.float32(p.g)), float(np.float32(p.rho0)), float(np.float32(p.chi)),
-                      float(np.float32(self.dtau_frac)), float(np.float32(p.weno_eps)))
+                      float(np.float32(self.dtau_frac)), float(np.float32(p.weno_eps)),
+                      float(np.float32(p.kappa)), float(np.float32(p.nu)))
         # inputs are rounded to Float32 first (what the host model holds), then promoted for the f64 oracle
         conv = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float32).astype(self.dtype))
         self._keep = []

@@ -229,3 +229,36 @@ def test_tma_kernels_equal_blocked_kernels(oracle_mod, monkeypatch, grid_type, N
         for _ in range(4):
             M.time_step(m)
     assert M.compare_states(rm_t, rm_b, include_halos=True, rtol=3e-6, atol=0.0, verbose=False, elementwise=1e-5)
+
+
+@pytest.mark.parametrize("grid_type,Nx,Ny,Nz", GRIDS)
+@pytest.mark.parametrize("closure", [1, 2])
+def test_vertical_diffusion_closures(oracle_mod, grid_type, Nx, Ny, Nz, closure):
+    """Row A13: VerticalScalarDiffusivity, explicit (tendency term) and vertically implicit (Thomas solve after
+    the AB2 update), with coefficients large enough to matter.  Same criterion as the baroclinic-state test:
+    as close to the Float64 oracle as the Float32 oracle is (x3), and within rtol wherever Float32 itself is."""
+    # strong mixing: K dt / dz^2 ~ 0.03 per step.  The Float32 oracle evaluates the smoothness indicators as sums of
+    # squares here (oracle_beta_form=1): on the mixed, very smooth velocity field the expanded form of the reference
+    # hits beta + eps == 0 and returns NaN in Float32 (deviation D1 of DESIGN.md; observed in this very test).
+    ph = PhysicsConfig(closure=closure, kappa=10.0, nu=50.0, oracle_beta_form=1)
+    rm, v32 = make_models(grid_type, Nx, Ny, Nz, 120.0, oracle_mod, physics=ph)
+    _, v64 = make_models(grid_type, Nx, Ny, Nz, 120.0, oracle_mod, physics=ph, dtype=np.float64, with_cuda=False)
+    _, v64_off = make_models(grid_type, Nx, Ny, Nz, 120.0, oracle_mod, dtype=np.float64, with_cuda=False)
+    for m in (rm, v32, v64, v64_off):
+        M.first_time_step(m)
+        for _ in range(4):
+            M.time_step(m)
+    bad = []
+    for n in ("u", "v", "w", "T", "S", "eta", "Gn_u", "Gn_v", "Gn_T", "Gn_S", "filt_U", "filt_V"):
+        t = v64.parent(n).astype(np.float64)
+        nrm = max(np.linalg.norm(t), 1e-300)
+        e32 = np.linalg.norm(v32.parent(n).astype(np.float64) - t) / nrm
+        ecu = np.linalg.norm(rm.parent(n).astype(np.float64) - t) / nrm
+        print(f"{n:8s} |cuda-f64|={ecu:.3e}  |f32-f64|={e32:.3e}")
+        if not (np.isfinite(ecu) and ecu <= max(RTOL, 3 * e32)):
+            bad.append((n, ecu, e32))
+    assert not bad, bad
+    # and the closure really did something (otherwise the comparison above proves nothing)
+    dT = np.linalg.norm(v64.interior("T") - v64_off.interior("T")) / np.linalg.norm(v64_off.interior("T"))
+    du = np.linalg.norm(v64.interior("u") - v64_off.interior("u")) / np.linalg.norm(v64_off.interior("u"))
+    assert dT > 1e-5 and du > 1e-2

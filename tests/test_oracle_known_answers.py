@@ -257,3 +257,34 @@ def test_deviation_D1_sum_of_squares_smoothness_is_within_tolerance(oracle_mod):
             M.time_step(m)
         ms.append(m)
     assert M.compare_states(ms[0], ms[1], include_halos=True, verbose=False, elementwise=1e-4)
+
+
+def test_vertical_diffusion_known_answers(oracle_mod):
+    """Row A13.  (i) implicit and explicit discretisations agree to O(dt^2) for a small step; (ii) both conserve the
+    column integral of a tracer exactly (no-flux walls); (iii) on uniform spacing cos(pi m (k+1/2)/Nz) is an exact
+    eigenvector of the discrete no-flux Laplacian with eigenvalue -(4/dz^2) sin^2(pi m / 2Nz), so one backward-Euler
+    step damps it by 1/(1 + dt K (4/dz^2) sin^2(pi m / 2Nz)) — and one forward-Euler step by 1 - dt K (...)."""
+    from gb25_b200.config import PhysicsConfig
+    g = grids.simple_latitude_longitude_grid(16, 16, 12)
+    # uniform vertical spacing for the closed form
+    dz = 10.0
+    zf = np.arange(-12, 1) * dz
+    g.z = grids._vertical(12, g.Hz, zf)
+    K, dt = 1e-2, 500.0
+    out = {}
+    for cl in (1, 2):
+        m = oracle_mod.OracleModel(oracle_mod.CPUOracle(np.float64), g, PhysicsConfig(closure=cl, kappa=K, nu=K))
+        m.clock.last_Δt = dt
+        k = np.arange(12)
+        mm = 3
+        mode = np.cos(np.pi * mm * (k + 0.5) / 12)[:, None, None]
+        M.set(m, T=10.0 + mode + 0 * m.interior("T"), S=35.0 + 0 * m.interior("S"))
+        col0 = m.interior("T").sum(axis=0)
+        M.first_time_step(m)
+        T = m.interior("T")
+        assert np.allclose(T.sum(axis=0), col0, rtol=1e-13)         # (ii)
+        out[cl] = T.copy()
+        amp = (T[:, 3, 3] - 10.0) / mode[:, 0, 0]
+        mu = dt * K * (4.0 / dz ** 2) * np.sin(np.pi * mm / 24) ** 2
+        assert np.allclose(amp, 1.0 / (1.0 + mu) if cl == 2 else 1.0 - mu, rtol=1e-9)          # (iii)
+    assert np.abs(out[1] - out[2]).max() < 2.0 * mu ** 2   # (i)
