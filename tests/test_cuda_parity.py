@@ -262,3 +262,76 @@ def test_vertical_diffusion_closures(oracle_mod, grid_type, Nx, Ny, Nz, closure)
     dT = np.linalg.norm(v64.interior("T") - v64_off.interior("T")) / np.linalg.norm(v64_off.interior("T"))
     du = np.linalg.norm(v64.interior("u") - v64_off.interior("u")) / np.linalg.norm(v64_off.interior("u"))
     assert dT > 1e-5 and du > 1e-2
+
+
+def test_baseline_config_c1_latlon_128x64x8_100_steps(oracle_mod):
+    """BASELINE.json configs[0]: baroclinic_instability_model on LatitudeLongitudeGrid 128x64x8, Float32,
+    1 Euler + 100 AB2 steps, reference state (T = S = 0, random u, v), against the oracle."""
+    rm, vm = make_models("simple_lat_lon", 128, 64, 8, 60.0, oracle_mod, state="zero_tracers")
+    M.first_time_step(rm); M.first_time_step(vm)
+    M.loop(rm, 100); M.loop(vm, 100)
+    assert rm.clock.iteration == vm.clock.iteration == 101
+    M.compare_states(rm, vm, include_halos=True, throw_error=True, rtol=RTOL, atol=0.0, elementwise=2e-4, verbose=False)
+
+
+def test_full_size_properties_tripolar_1440x600x50():
+    """BASELINE.json configs[1] at full size (no oracle: it would take minutes): size-independent properties.
+    (i) state stays finite; (ii) masks hold: u, v, T, S vanish on every immersed / peripheral node; (iii) halos are
+    consistent: periodic wrap and the zipper fold relations hold on the final state; (iv) two identical runs are
+    bit-identical (no races, no uninitialised reads); (v) G halos stay identically zero."""
+    import bench
+    outs = []
+    for rep in range(2):
+        m = M.baroclinic_instability_model(M.B200(0), 1440, 600, 50, Δt=60.0, grid_type="gaussian_islands")
+        bench.synthetic_state(m)
+        M.first_time_step(m)
+        M.loop(m, 3)
+        outs.append({n: m.parent(n) for n in ("u", "v", "T", "eta", "Gn_T", "Gn_u")})
+        g = m.grid
+        m.close()
+    a, b = outs
+    for n in a:
+        assert np.isfinite(a[n]).all(), n
+        assert np.array_equal(a[n].view(np.uint32), b[n].view(np.uint32)), f"{n}: run-to-run difference"
+    Hx, Hy, Hz, Nx, Ny, Nz = g.Hx, g.Hy, g.Hz, g.Nx, g.Ny, g.Nz
+    zc = np.float32(g.z["z_c"])[Hz:Hz + Nz]
+    kb = (zc[None, None, :] <= np.float32(g.bottom_height)[:, :, None]).sum(-1)
+    kbi = kb[Hy:Hy + Ny, Hx:Hx + Nx]
+    solid = np.arange(1, Nz + 1)[:, None, None] <= kbi[None]
+    assert solid.sum() > 1e5
+    T = a["T"][Hz:Hz + Nz, Hy:Hy + Ny, Hx:Hx + Nx]
+    u = a["u"][Hz:Hz + Nz, Hy:Hy + Ny, Hx:Hx + Nx]
+    assert (T[solid] == 0).all() and (u[solid] == 0).all()
+    kbw = kb[Hy:Hy + Ny, Hx - 1:Hx + Nx - 1]
+    assert (u[np.arange(1, Nz + 1)[:, None, None] <= kbw[None]] == 0).all()        # west neighbour solid => u masked
+    for n in ("u", "v", "T"):
+        p = a[n]
+        assert np.array_equal(p[:, :, :Hx], p[:, :, Nx:Nx + Hx]) and np.array_equal(p[:, :, Nx + Hx:], p[:, :, Hx:2 * Hx])
+    kk = slice(Hz, Hz + Nz)
+    i = np.arange(1, Nx + 1)
+    for mm in (1, 4, 8):
+        assert np.array_equal(a["T"][kk, Ny + mm + Hy - 1, i + Hx - 1], a["T"][kk, Ny - mm + Hy - 1, (Nx - i + 1) + Hx - 1])
+        assert np.array_equal(a["v"][kk, Ny + mm + Hy - 1, i + Hx - 1], -a["v"][kk, Ny - mm + 1 + Hy - 1, (Nx - i + 1) + Hx - 1])
+    for n in ("Gn_T", "Gn_u"):
+        p = a[n].copy()
+        p[Hz:Hz + Nz, Hy:Hy + Ny, Hx:Hx + Nx] = 0
+        assert not p.any(), f"{n}: halo of a tendency array was written"
+
+
+def test_full_size_free_surface_volume_conservation_latlon_1440x600x50():
+    """Full-size lat-lon run: the split-explicit substeps conserve sum(Az*eta) (no flow through the walls,
+    periodic in x) — checked to Float32 round-off over 5 steps."""
+    import bench
+    m = M.baroclinic_instability_model(M.B200(0), 1440, 600, 50, Δt=60.0, grid_type="simple_lat_lon")
+    bench.synthetic_state(m)
+    g = m.grid
+    az = np.float32(g.metrics["az_cc"])[g.Hy:g.Hy + g.Ny, g.Hx:g.Hx + g.Nx].astype(np.float64)
+    M.first_time_step(m)
+    v0 = (m.interior("eta")[0].astype(np.float64) * az).sum()
+    M.loop(m, 5)
+    eta = m.interior("eta")[0].astype(np.float64)
+    v1 = (eta * az).sum()
+    scale = (np.abs(eta) * az).sum()
+    assert np.isfinite(eta).all() and scale > 0
+    assert abs(v1 - v0) <= 2e-5 * scale
+    m.close()
