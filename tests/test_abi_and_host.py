@@ -97,3 +97,24 @@ def test_isapprox_is_norm_based_like_julia():
     assert not M.compare_parent("x", a, b, rtol=1e-3, atol=0, verbose=False, elementwise=1e-4)
     c = a.copy(); c[0, 0, 0] = np.nan
     assert not M.compare_parent("x", a, c, rtol=1.0, atol=0, verbose=False)
+
+
+def test_state_dump_and_global_reassembly(tmp_path, oracle_mod):
+    """sharded_io: per-rank dump + offline reassembly (format of /root/reference/src/sharded_io.jl), exercised on the
+    CPU with the oracle model in the model seat (the dump code only needs parent()/interior())."""
+    from gb25_b200 import sharded_io as IO
+    m = M.baroclinic_instability_model(oracle_mod.CPUOracle(np.float32), 32, 16, 4, Δt=60.0, model_cls=oracle_mod.OracleModel)
+    rng = np.random.default_rng(0)
+    M.set(m, u=1e-3 * rng.random(m.interior("u").shape), v=1e-3 * rng.random(m.interior("v").shape))
+    M.first_time_step(m)
+    path = IO.save_model_state(str(tmp_path), m, label="first_loop")
+    assert os.path.basename(path) == "fields_rank0.npz"
+    allf = IO.load_all_fields(str(tmp_path), label="first_loop")
+    assert allf["iteration"] == 1 and allf["time"] == 60.0
+    for n in ("u", "v", "w", "T", "S", "eta"):
+        assert np.array_equal(allf[n], m.interior(n))
+    m2 = M.baroclinic_instability_model(oracle_mod.CPUOracle(np.float32), 32, 16, 4, Δt=60.0, model_cls=oracle_mod.OracleModel)
+    IO.load_model_state(str(tmp_path), m2, label="first_loop")
+    M.time_step(m); M.time_step(m2)
+    for n in ("u", "v", "T", "eta", "Gn_u", "Gm_T"):
+        assert np.array_equal(m.parent(n), m2.parent(n)), n
