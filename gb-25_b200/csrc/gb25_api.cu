@@ -311,6 +311,8 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     h->use_fused = !(e && e[0] == '0');
     const char* t = getenv("GB25_TMA");
     h->use_tma = !(t && t[0] == '0');
+    const char* tt = getenv("GB25_TMA_TRACER");
+    h->use_tma_tracer = !(tt && tt[0] == '0');
   }
   DevFields& f = h->f;
   f.u = h->field_ptr[GB25_U]; f.v = h->field_ptr[GB25_V]; f.w = h->field_ptr[GB25_W];

@@ -70,6 +70,7 @@ struct gb25_handle {
   long graph_launches = 0;
   bool use_fused = true;
   bool use_tma = true;
+  bool use_tma_tracer = true;
   void* tma = nullptr;   // TMA tensor maps (gb25_tend_tma.cu)
 
   inline void count_launch() { launches++; }
@@ -117,6 +118,7 @@ void launch_aux_columns(Handle* h);
 void launch_generic_list(Handle* h, bool momentum, bool tracers);   // gb25_tend_v2.cu
 void launch_momentum_tendency_tma(Handle* h);   // gb25_tend_tma.cu
 bool tma_available(Handle* h);
+void launch_tracer_tendency_tma(Handle* h);
 void tma_free(Handle* h);           // gb25_tend_v2.cu: w + zeta + flux divergences in one column pass
 void launch_momentum_tendency(Handle* h);
 void launch_ab2_columns(Handle* h, float dt, float chi);

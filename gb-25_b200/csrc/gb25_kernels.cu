@@ -234,7 +234,8 @@ void launch_tracer_tendency_v1(Handle* h) {
   h->count_launch();
 }
 void launch_tracer_tendency(Handle* h) {
-  if (h->use_fused && h->g.Nx % 4 == 0) { launch_generic_list(h, false, true); launch_tracer_tendency_v2(h); }
+  if (h->use_fused && h->use_tma && h->use_tma_tracer && h->g.Nx % 4 == 0 && tma_available(h)) { launch_generic_list(h, false, true); launch_tracer_tendency_tma(h); }
+  else if (h->use_fused && h->g.Nx % 4 == 0) { launch_generic_list(h, false, true); launch_tracer_tendency_v2(h); }
   else launch_tracer_tendency_v1(h);
 }
 

@@ -364,6 +364,177 @@ k_gv_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
   }
 }
 
+// =====================================================================================
+// Tracer tendencies (row A6), TMA-staged.  CTA = 32 x 16 columns; 128 consumer threads, each owning a 2 x 2 patch
+// of columns so that the x- and y-face fluxes inside the patch are computed once (16 reconstructions for 4 cells:
+// 4.0 per cell instead of 4.5 in the register-blocked kernel and 6 in the per-cell one); one tracer per blockIdx.z.
+// Same ring / barrier scheme as the momentum kernels; generic cells belong to k_generic_list.
+// =====================================================================================
+#define TR_TX 32
+#define TR_TY 16
+#define TR_PT (TR_TX + 8)
+#define TR_PU (TR_TX + 4)
+#define TR_PV (TR_TX)
+#define TR_OFF_T 0
+#define TR_OFF_U (TR_OFF_T + TR_PT * (TR_TY + 8))
+#define TR_OFF_V (TR_OFF_U + TR_PU * TR_TY)
+#define TR_OFF_W (TR_OFF_V + TR_PV * (TR_TY + 1))
+#define TR_STAGE (TR_OFF_W + TR_PV * TR_TY)
+#define TR_CW 4   // consumer warps
+
+struct TmaMaps5 { CUtensorMap m[5]; };   // T, S, u, v, w
+
+__device__ __forceinline__ float weno5_selp(const float* q, bool left, float eps) {   // q[0..5], face between q[2], q[3]
+  const float v0 = left ? q[0] : q[5], v1 = left ? q[1] : q[4], v2 = left ? q[2] : q[3], v3 = left ? q[3] : q[2], v4 = left ? q[4] : q[1];
+  return weno5(v0, v1, v2, v3, v4, eps);
+}
+
+#ifndef TR_MINB
+#define TR_MINB 3
+#endif
+__global__ void __launch_bounds__(160, TR_MINB)
+k_tracer_tma(DevGrid g, const __grid_constant__ TmaMaps5 tm, const float* __restrict__ T0, const float* __restrict__ T1,
+             float* __restrict__ G0, float* __restrict__ G1, const float* __restrict__ carry0, const float* __restrict__ carry1) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t bar[TMA_NST], ebar[TMA_NST];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
+  const int i0 = blockIdx.x * TR_TX + 1, j0 = blockIdx.y * TR_TY + 1;
+  const int I0 = i0 + g.Hx - 1, J0 = j0 + g.Hy - 1;
+  const int tr = blockIdx.z;
+  const int PX = g.PX, n2 = g.n2, Nz = g.Nz;
+  const float eps = g.eps;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TMA_NST; s++) { mbar_init(&bar[s], 1); mbar_init(&ebar[s], TR_CW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (ty >= 8) {   // ===== producer warp
+    if (tid == 128)
+      for (int k = 1; k <= Nz; k++) {
+        const int s = (k - 1) % TMA_NST;
+        if (k > TMA_NST) mbar_wait(&ebar[s], (((k - 1) / TMA_NST) - 1) & 1);
+        float* sm = smem + s * TR_STAGE;
+        const int K = k + g.Hz - 1;
+        mbar_expect_tx(&bar[s], TR_STAGE * sizeof(float));
+        tma_load_3d(sm + TR_OFF_T, &tm.m[tr], &bar[s], I0 - 4, J0 - 4, K);
+        tma_load_3d(sm + TR_OFF_U, &tm.m[2], &bar[s], I0, J0, K);
+        tma_load_3d(sm + TR_OFF_V, &tm.m[3], &bar[s], I0, J0, K);
+        tma_load_3d(sm + TR_OFF_W, &tm.m[4], &bar[s], I0, J0, K + 1);
+      }
+    return;
+  }
+  const float* __restrict__ T = tr == 0 ? T0 : T1;
+  float* __restrict__ G = tr == 0 ? G0 : G1;
+  const float* __restrict__ carry = tr == 0 ? carry0 : carry1;
+  const int lx = 2 * tx, ly = 2 * ty;                       // tile-local column / row of the patch
+  const int ic = min(i0 + lx, g.Nx - 1), jc = min(j0 + ly, g.Ny - 1);   // clamped patch origin (for the hoisted loads)
+  const bool vx = (i0 + lx + 1) <= g.Nx;
+  bool vrow[2] = {vx && (j0 + ly) <= g.Ny, vx && (j0 + ly + 1) <= g.Ny};
+  const int q2 = id2(g, ic, jc);
+  // ---- hoisted 2-D data
+  float dyf[2][3], dxf[3][2], az[2][2];
+  int kbc[2][2], kg[2], kz[2];
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+#pragma unroll
+    for (int e = 0; e < 3; e++) dyf[r][e] = g.dyfc[q2 + r * PX + e];
+#pragma unroll
+    for (int c = 0; c < 2; c++) { az[r][c] = g.azcc[q2 + r * PX + c]; kbc[r][c] = g.kb[q2 + r * PX + c]; }
+    kg[r] = g.kgen2[q2 + r * PX]; kz[r] = g.kzero2[q2 + r * PX];
+  }
+#pragma unroll
+  for (int e = 0; e < 3; e++) { dxf[e][0] = g.dxcf[q2 + e * PX]; dxf[e][1] = g.dxcf[q2 + e * PX + 1]; }
+  // ---- vertical register windows W[r][c][m] = T(i, j, k-3+m)
+  size_t q3 = q2 + (size_t)n2 * g.Hz;
+  float W[2][2][7];
+#pragma unroll
+  for (int m = 0; m < 7; m++)
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(T + q3 + (ptrdiff_t)(m - 3) * n2 + r * PX));
+      W[r][0][m] = a.x; W[r][1][m] = a.y;
+    }
+  float Fz[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  const int oT = (ly + 4) * TR_PT + (lx + 4), oU = ly * TR_PU + lx, oV = ly * TR_PV + lx;
+  for (int k = 1; k <= Nz; k++, q3 += n2) {
+    const int s = (k - 1) % TMA_NST;
+    mbar_wait(&bar[s], ((k - 1) / TMA_NST) & 1);
+    const float* sm = smem + s * TR_STAGE;
+    const bool fast0 = k > kg[0], fast1 = k > kg[1];
+    float out[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    if (fast0 || fast1) {
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+        if (k == kg[r] + 1 && kg[r] > 0) { Fz[r][0] = carry[q2 + r * PX]; Fz[r][1] = carry[q2 + r * PX + 1]; }
+      const float dz = g.dzc[k + g.Hz - 1];
+      const float* St = sm + TR_OFF_T + oT;
+      // ---- x faces: 3 per row.  rT[r][n] <-> local column lx-4+n
+      float fx[2][3];
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        float rT[10];
+#pragma unroll
+        for (int b = 0; b < 5; b++) {
+          const float2 a = *reinterpret_cast<const float2*>(St + r * TR_PT - 4 + 2 * b);
+          rT[2 * b] = a.x; rT[2 * b + 1] = a.y;
+        }
+        const float2 ua = *reinterpret_cast<const float2*>(sm + TR_OFF_U + oU + r * TR_PU);
+        const float ub = sm[TR_OFF_U + oU + r * TR_PU + 2];
+        const float uu[3] = {ua.x, ua.y, ub};
+#pragma unroll
+        for (int e = 0; e < 3; e++) fx[r][e] = dyf[r][e] * dz * uu[e] * weno5_selp(&rT[e + 1], uu[e] > 0.f, eps);
+      }
+      // ---- y faces: 3 per column.  cT[m][c] <-> local row ly-4+m
+      float fy[3][2];
+      {
+        float cT[10][2];
+#pragma unroll
+        for (int m = 0; m < 10; m++) {
+          const float2 a = *reinterpret_cast<const float2*>(St + (m - 4) * TR_PT);
+          cT[m][0] = a.x; cT[m][1] = a.y;
+        }
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+          const float2 va = *reinterpret_cast<const float2*>(sm + TR_OFF_V + oV + e * TR_PV);
+          const float vv[2] = {va.x, va.y};
+#pragma unroll
+          for (int c = 0; c < 2; c++) {
+            const float q[6] = {cT[e + 1][c], cT[e + 2][c], cT[e + 3][c], cT[e + 4][c], cT[e + 5][c], cT[e + 6][c]};
+            fy[e][c] = dxf[e][c] * dz * vv[c] * weno5_selp(q, vv[c] > 0.f, eps);
+          }
+        }
+      }
+      // ---- z: top faces from the register windows; bottom fluxes are carried
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const float2 wa = *reinterpret_cast<const float2*>(sm + TR_OFF_W + oV + r * TR_PV);
+        const float ww[2] = {wa.x, wa.y};
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const int Bt = zbuf(g, kbc[r][c], k + 1, 3);
+          const float ft = az[r][c] * ww[c] * weno_sel_B3(W[r][c][1], W[r][c][2], W[r][c][3], W[r][c][4], W[r][c][5], W[r][c][6], Bt, ww[c] > 0.f, eps);
+          const float rV = 1.f / (az[r][c] * dz);
+          out[r][c] = -(rV * (((fx[r][c + 1] - fx[r][c]) + (fy[r + 1][c] - fy[r][c])) + (ft - Fz[r][c])));
+          Fz[r][c] = ft;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const bool fast = r == 0 ? fast0 : fast1;
+      if (k <= kz[r]) { Fz[r][0] = 0.f; Fz[r][1] = 0.f; out[r][0] = 0.f; out[r][1] = 0.f; }
+      if (vrow[r] && (fast || k <= kz[r])) *reinterpret_cast<float2*>(G + q3 + r * PX) = make_float2(out[r][0], out[r][1]);
+      const float2 a = __ldg(reinterpret_cast<const float2*>(T + q3 + (size_t)4 * n2 + r * PX));
+#pragma unroll
+      for (int m = 0; m < 6; m++) { W[r][0][m] = W[r][0][m + 1]; W[r][1][m] = W[r][1][m + 1]; }
+      W[r][0][6] = a.x; W[r][1][6] = a.y;
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&ebar[s]);
+  }
+}
+
 // ----------------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -389,7 +560,7 @@ static bool make_map(const DevGrid& g, const float* base, int bx, int by, CUtens
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct TmaState { bool ready = false, ok = false; TmaMaps7 gu, gv; };
+struct TmaState { bool ready = false, ok = false; TmaMaps7 gu, gv; TmaMaps5 tr; };
 static TmaState* tma_state(Handle* h) {
   if (!h->tma) h->tma = new TmaState();
   TmaState* t = (TmaState*)h->tma;
@@ -413,7 +584,13 @@ static TmaState* tma_state(Handle* h) {
   ok &= make_map(g, h->dxU, TX, TY + 8, &t->gv.m[4]);
   ok &= make_map(g, h->f.w, TX, TY + 8, &t->gv.m[5]);
   ok &= make_map(g, h->f.p, TX, TY + 8, &t->gv.m[6]);
+  ok &= make_map(g, h->f.T, TR_TX + 8, TR_TY + 8, &t->tr.m[0]);
+  ok &= make_map(g, h->f.S, TR_TX + 8, TR_TY + 8, &t->tr.m[1]);
+  ok &= make_map(g, h->f.u, TR_TX + 4, TR_TY, &t->tr.m[2]);
+  ok &= make_map(g, h->f.v, TR_TX, TR_TY + 1, &t->tr.m[3]);
+  ok &= make_map(g, h->f.w, TR_TX, TR_TY, &t->tr.m[4]);
   if (ok) {
+    ok &= cudaFuncSetAttribute(k_tracer_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * TR_STAGE * (int)sizeof(float)) == cudaSuccess;
     ok &= cudaFuncSetAttribute(k_gu_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GU_STAGE * (int)sizeof(float)) == cudaSuccess;
     ok &= cudaFuncSetAttribute(k_gv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GV_STAGE * (int)sizeof(float)) == cudaSuccess;
   }
@@ -432,5 +609,14 @@ void launch_momentum_tendency_tma(Handle* h) {
   h->count_launch();
   { StageScope ts(h, "kernel:k_gv_tma");
   k_gv_tma<<<gr, b, TMA_NST * GV_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gv, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[1], h->carry[1]); }
+  h->count_launch();
+}
+
+void launch_tracer_tendency_tma(Handle* h) {
+  TmaState* t = tma_state(h);
+  const DevGrid& g = h->g;
+  dim3 b(16, 10), gr((g.Nx + TR_TX - 1) / TR_TX, (g.Ny + TR_TY - 1) / TR_TY, 2);
+  StageScope ts(h, "kernel:k_tracer_tma");
+  k_tracer_tma<<<gr, b, TMA_NST * TR_STAGE * sizeof(float), h->stream>>>(g, t->tr, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3], h->carry[2], h->carry[3]);
   h->count_launch();
 }
