@@ -207,6 +207,9 @@ extern "C" int gb25_destroy(gb25_handle* h) {
   if (h->loop_start) cudaEventDestroy(h->loop_start);
   if (h->loop_stop) cudaEventDestroy(h->loop_stop);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
   return GB25_OK;
 }
@@ -253,6 +256,9 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     return GB25_OK;
   };
   CKC(ckcuda(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
+  CKC(ckcuda(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking), "cudaStreamCreate"));
+  CKC(ckcuda(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), "cudaEventCreate"));
+  CKC(ckcuda(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming), "cudaEventCreate"));
   CKC(ckcuda(cudaEventCreate(&h->loop_start), "cudaEventCreate"));
   CKC(ckcuda(cudaEventCreate(&h->loop_stop), "cudaEventCreate"));
   DevGrid& g = h->g;
@@ -311,6 +317,8 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     h->use_fused = !(e && e[0] == '0');
     const char* t = getenv("GB25_TMA");
     h->use_tma = !(t && t[0] == '0');
+    const char* ov = getenv("GB25_OVERLAP");
+    h->use_overlap = (ov && ov[0] == '1');   // measured: 5.33 vs 5.36 ms/step at C2 — within noise, so off by default
     const char* tt = getenv("GB25_TMA_TRACER");
     h->use_tma_tracer = !(tt && tt[0] == '0');
   }
@@ -428,11 +436,28 @@ static void stage_initialize(Handle* h) {
   HaloSpec sb[2] = {{h->f.bu, 1, 0, 0, -1.f}, {h->f.bv, 0, 1, 0, -1.f}};
   launch_fill_halo(h, sb, 2, false);
 }
+struct StreamSwap {   // launch on another stream for the lifetime of the object
+  Handle* h; cudaStream_t saved;
+  StreamSwap(Handle* h_, cudaStream_t s) : h(h_), saved(h_->stream) { h->stream = s; }
+  ~StreamSwap() { h->stream = saved; }
+};
 // fused step path: identical results, fewer passes over the 3-D state (see gb25_kernels.cu "Fused step path")
 static void one_time_step_fused(Handle* h, float dt, float chi) {
   DevFields& f = h->f;
   { StageScope t(h, "ab2_step_fields"); launch_ab2_fused(h, dt, chi); }
   if (h->cfg.closure == 2) { StageScope t(h, "vertical_diffusion"); launch_implicit_columns(h, dt, true); }
+  // T and S are final once the AB2 update (and the implicit solve) are done: their halo fill and the hydrostatic
+  // pressure scan do not depend on the barotropic solve, so they run on a second stream underneath the 43 small,
+  // L2-bound substep kernels (single-tile handles only: the tile exchange numbers its phases on one stream).
+  const bool overlap = h->use_overlap && !h->ex.on;
+  if (overlap) {
+    cudaEventRecord(h->ev_fork, h->stream);
+    cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+    StreamSwap sw(h, h->stream2);
+    { StageScope t(h, "fill_halo_regions_TS"); HaloSpec s3[2] = {{f.T, 0, 0, 0, 1.f}, {f.S, 0, 0, 0, 1.f}}; launch_fill_halo(h, s3, 2, true); }
+    { StageScope t(h, "update_hydrostatic_pressure"); launch_compute_p(h); }
+    cudaEventRecord(h->ev_join, h->stream2);
+  }
   {
     StageScope t(h, "split_explicit_free_surface");
     HaloSpec sg[2] = {{f.gU, 1, 0, 0, -1.f}, {f.gV, 0, 1, 0, -1.f}};
@@ -449,8 +474,20 @@ static void one_time_step_fused(Handle* h, float dt, float chi) {
     std::swap(f.gn[q], f.gm[q]);
     std::swap(h->field_ptr[GB25_GN_U + q], h->field_ptr[GB25_GM_U + q]);
   }
-  fill_prognostic(h);
-  stage_aux(h);
+  if (overlap) {
+    {
+      StageScope t(h, "fill_halo_regions");
+      HaloSpec s3[2] = {{f.u, 1, 0, 0, -1.f}, {f.v, 0, 1, 0, -1.f}};
+      launch_fill_halo(h, s3, 2, true);
+      HaloSpec s2[3] = {{f.eta, 0, 0, 1, 1.f}, {f.bu, 1, 0, 0, -1.f}, {f.bv, 0, 1, 0, -1.f}};
+      launch_fill_halo(h, s2, 3, false);
+    }
+    { StageScope t(h, "compute_w_from_continuity"); launch_aux_columns(h); }
+    cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+  } else {
+    fill_prognostic(h);
+    stage_aux(h);
+  }
   stage_tend(h);
 }
 static void one_time_step(Handle* h, float dt, bool euler) {

@@ -70,6 +70,9 @@ struct gb25_handle {
   long graph_launches = 0;
   bool use_fused = true;
   bool use_tma = true;
+  bool use_overlap = false;            // run the T,S halo fill + hydrostatic pressure on a second stream during the substeps
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_tma_tracer = true;
   void* tma = nullptr;   // TMA tensor maps (gb25_tend_tma.cu)
 
