@@ -18,6 +18,7 @@
 
 #include "gb25_internal.h"
 #include "gb25_tend_generic.cuh"
+#include "gb25_packed.cuh"
 
 #define TMA_TX 32
 #define TMA_TY 8
@@ -469,55 +470,59 @@ k_tracer_tma(DevGrid g, const __grid_constant__ TmaMaps5 tm, const float* __rest
         if (k == kg[r] + 1 && kg[r] > 0) { Fz[r][0] = carry[q2 + r * PX]; Fz[r][1] = carry[q2 + r * PX + 1]; }
       const float dz = g.dzc[k + g.Hz - 1];
       const float* St = sm + TR_OFF_T + oT;
-      // ---- x faces: 3 per row.  rT[r][n] <-> local column lx-4+n
-      float fx[2][3];
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        float rT[10];
-#pragma unroll
-        for (int b = 0; b < 5; b++) {
-          const float2 a = *reinterpret_cast<const float2*>(St + r * TR_PT - 4 + 2 * b);
-          rT[2 * b] = a.x; rT[2 * b + 1] = a.y;
-        }
-        const float2 ua = *reinterpret_cast<const float2*>(sm + TR_OFF_U + oU + r * TR_PU);
-        const float ub = sm[TR_OFF_U + oU + r * TR_PU + 2];
-        const float uu[3] = {ua.x, ua.y, ub};
-#pragma unroll
-        for (int e = 0; e < 3; e++) fx[r][e] = dyf[r][e] * dz * uu[e] * weno5_selp(&rT[e + 1], uu[e] > 0.f, eps);
-      }
-      // ---- y faces: 3 per column.  cT[m][c] <-> local row ly-4+m
-      float fy[3][2];
+      // All reconstructions are evaluated two at a time with packed FP32x2 arithmetic (gb25_packed.cuh):
+      // x faces pair the two rows of the patch, y and z faces pair its two columns.
+      // ---- x faces: 3 per row.  rT[n] = (row 0, row 1) at local column lx-4+n
+      float2 fx[3];
       {
-        float cT[10][2];
+        float2 rT[10];
 #pragma unroll
-        for (int m = 0; m < 10; m++) {
-          const float2 a = *reinterpret_cast<const float2*>(St + (m - 4) * TR_PT);
-          cT[m][0] = a.x; cT[m][1] = a.y;
-        }
+        for (int n = 0; n < 10; n++) rT[n] = make_float2(St[n - 4], St[TR_PT + n - 4]);
 #pragma unroll
         for (int e = 0; e < 3; e++) {
-          const float2 va = *reinterpret_cast<const float2*>(sm + TR_OFF_V + oV + e * TR_PV);
-          const float vv[2] = {va.x, va.y};
-#pragma unroll
-          for (int c = 0; c < 2; c++) {
-            const float q[6] = {cT[e + 1][c], cT[e + 2][c], cT[e + 3][c], cT[e + 4][c], cT[e + 5][c], cT[e + 6][c]};
-            fy[e][c] = dxf[e][c] * dz * vv[c] * weno5_selp(q, vv[c] > 0.f, eps);
-          }
+          const float2 uu = make_float2(sm[TR_OFF_U + oU + e], sm[TR_OFF_U + oU + TR_PU + e]);
+          const float2 av = pmul(pmuls(make_float2(dyf[0][e], dyf[1][e]), dz), uu);
+          fx[e] = pmul(av, pweno5_sel(&rT[e + 1], uu.x > 0.f, uu.y > 0.f, eps));
         }
       }
-      // ---- z: top faces from the register windows; bottom fluxes are carried
+      // ---- y faces: 3 per column.  cT[m] = (col 0, col 1) at local row ly-4+m
+      float2 fy[3];
+      {
+        float2 cT[10];
+#pragma unroll
+        for (int m = 0; m < 10; m++) cT[m] = *reinterpret_cast<const float2*>(St + (m - 4) * TR_PT);
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+          const float2 vv = *reinterpret_cast<const float2*>(sm + TR_OFF_V + oV + e * TR_PV);
+          const float2 av = pmul(pmuls(make_float2(dxf[e][0], dxf[e][1]), dz), vv);
+          fy[e] = pmul(av, pweno5_sel(&cT[e + 1], vv.x > 0.f, vv.y > 0.f, eps));
+        }
+      }
+      // ---- z: top faces from the register windows (pairs of columns); bottom fluxes are carried
 #pragma unroll
       for (int r = 0; r < 2; r++) {
-        const float2 wa = *reinterpret_cast<const float2*>(sm + TR_OFF_W + oV + r * TR_PV);
-        const float ww[2] = {wa.x, wa.y};
+        const float2 ww = *reinterpret_cast<const float2*>(sm + TR_OFF_W + oV + r * TR_PV);
+        const int B0 = zbuf(g, kbc[r][0], k + 1, 3), B1 = zbuf(g, kbc[r][1], k + 1, 3);
+        float2 rec;
+        if (B0 == 3 && B1 == 3) {
+          float2 q[6];
 #pragma unroll
-        for (int c = 0; c < 2; c++) {
-          const int Bt = zbuf(g, kbc[r][c], k + 1, 3);
-          const float ft = az[r][c] * ww[c] * weno_sel_B3(W[r][c][1], W[r][c][2], W[r][c][3], W[r][c][4], W[r][c][5], W[r][c][6], Bt, ww[c] > 0.f, eps);
-          const float rV = 1.f / (az[r][c] * dz);
-          out[r][c] = -(rV * (((fx[r][c + 1] - fx[r][c]) + (fy[r + 1][c] - fy[r][c])) + (ft - Fz[r][c])));
-          Fz[r][c] = ft;
+          for (int m = 0; m < 6; m++) q[m] = make_float2(W[r][0][m + 1], W[r][1][m + 1]);
+          rec = pweno5_sel(q, ww.x > 0.f, ww.y > 0.f, eps);
+        } else {
+          rec.x = weno_sel_B3(W[r][0][1], W[r][0][2], W[r][0][3], W[r][0][4], W[r][0][5], W[r][0][6], B0, ww.x > 0.f, eps);
+          rec.y = weno_sel_B3(W[r][1][1], W[r][1][2], W[r][1][3], W[r][1][4], W[r][1][5], W[r][1][6], B1, ww.y > 0.f, eps);
         }
+        const float2 azp = make_float2(az[r][0], az[r][1]);
+        const float2 ft = pmul(pmul(azp, ww), rec);
+        const float2 rV = prcp_exact(pmuls(azp, dz));
+        const float fxr0 = r == 0 ? fx[0].x : fx[0].y, fxr1 = r == 0 ? fx[1].x : fx[1].y, fxr2 = r == 0 ? fx[2].x : fx[2].y;
+        const float2 dfx = make_float2(fxr1 - fxr0, fxr2 - fxr1);
+        const float2 dfy = psub(fy[r + 1], fy[r]);
+        const float2 fzo = make_float2(Fz[r][0], Fz[r][1]);
+        const float2 o = pmul(rV, padd(padd(dfx, dfy), psub(ft, fzo)));
+        out[r][0] = -o.x; out[r][1] = -o.y;
+        Fz[r][0] = ft.x; Fz[r][1] = ft.y;
       }
     }
 #pragma unroll
