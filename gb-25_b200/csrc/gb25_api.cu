@@ -319,6 +319,8 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     h->use_tma = !(t && t[0] == '0');
     const char* ov = getenv("GB25_OVERLAP");
     h->use_overlap = (ov && ov[0] == '1');   // measured: 5.33 vs 5.36 ms/step at C2 — within noise, so off by default
+    const char* pk = getenv("GB25_PACKED");
+    h->use_packed = !(pk && pk[0] == '0');
     const char* tt = getenv("GB25_TMA_TRACER");
     h->use_tma_tracer = !(tt && tt[0] == '0');
   }

@@ -74,6 +74,7 @@ struct gb25_handle {
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_tma_tracer = true;
+  bool use_packed = true;              // FP32x2 (FFMA2) momentum kernels
   void* tma = nullptr;   // TMA tensor maps (gb25_tend_tma.cu)
 
   inline void count_launch() { launches++; }

@@ -366,6 +366,246 @@ k_gv_tma(DevGrid g, const DevGrid* __restrict__ gp, const __grid_constant__ TmaM
 }
 
 // =====================================================================================
+// Packed (FP32x2) variants of the momentum kernels: the same tiles, ring and barriers, but 128 consumer threads, each
+// owning TWO x-adjacent cells whose arithmetic runs two lanes wide in FFMA2 / FADD2 / FMUL2 (gb25_packed.cuh).
+// Windows across y and z are natural float2 loads (the pair is contiguous in shared memory); windows along x are
+// assembled from two 32-bit loads when the offset is odd.  Divisions by metrics use reciprocals hoisted out of the
+// k loop (one IEEE division per column instead of five per cell and level).
+// =====================================================================================
+__device__ __forceinline__ float2 ldp(const float* p) { return make_float2(p[0], p[1]); }                       // any alignment
+__device__ __forceinline__ float2 ldpa(const float* p) { return *reinterpret_cast<const float2*>(p); }           // 8-byte aligned
+__device__ __forceinline__ float2 psym4(float2 q0, float2 q1, float2 q2, float2 q3, int B) {
+  return B >= 2 ? pfmas(q0, -1.f / 12.f, pfmas(q1, 7.f / 12.f, pfmas(q2, 7.f / 12.f, pmuls(q3, -1.f / 12.f))))
+                : pmuls(padd(q1, q2), 0.5f);
+}
+__device__ __forceinline__ float2 pneg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 pweno5_fs_sel(const float2* q, const float2* s, bool lx, bool ly, float eps) {
+  return pweno5_fs(psel(q[0], q[5], lx, ly), psel(q[1], q[4], lx, ly), psel(q[2], q[3], lx, ly), psel(q[3], q[2], lx, ly), psel(q[4], q[1], lx, ly),
+                   psel(s[0], s[5], lx, ly), psel(s[1], s[4], lx, ly), psel(s[2], s[3], lx, ly), psel(s[3], s[2], lx, ly), psel(s[4], s[1], lx, ly), eps);
+}
+__device__ __forceinline__ float2 pweno5_vs_sel(const float2* q, const float2* s, const float2* r, bool lx, bool ly, float eps) {
+  return pweno5_vs(psel(q[0], q[5], lx, ly), psel(q[1], q[4], lx, ly), psel(q[2], q[3], lx, ly), psel(q[3], q[2], lx, ly), psel(q[4], q[1], lx, ly),
+                   psel(s[0], s[5], lx, ly), psel(s[1], s[4], lx, ly), psel(s[2], s[3], lx, ly), psel(s[3], s[2], lx, ly), psel(s[4], s[1], lx, ly),
+                   psel(r[0], r[5], lx, ly), psel(r[1], r[4], lx, ly), psel(r[2], r[3], lx, ly), psel(r[3], r[2], lx, ly), psel(r[4], r[1], lx, ly), eps);
+}
+// vertical reconstruction of a pair from the two register windows; order reduction falls back to the scalar code
+__device__ __forceinline__ float2 pvert(const float (&A)[7], const float (&B)[7], int BA, int BB, float2 wt, float eps) {
+  if (BA == 3 && BB == 3) {
+    float2 q[6];
+#pragma unroll
+    for (int m = 0; m < 6; m++) q[m] = make_float2(A[m + 1], B[m + 1]);
+    return pweno5_sel(q, wt.x > 0.f, wt.y > 0.f, eps);
+  }
+  return make_float2(weno_sel_B3(A[1], A[2], A[3], A[4], A[5], A[6], BA, wt.x > 0.f, eps),
+                     weno_sel_B3(B[1], B[2], B[3], B[4], B[5], B[6], BB, wt.y > 0.f, eps));
+}
+
+#ifndef MOM_MINB
+#define MOM_MINB 3
+#endif
+template <int DIR>
+__global__ void __launch_bounds__(160, MOM_MINB)
+k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const float* __restrict__ own_g, float* __restrict__ G,
+             const float* __restrict__ carry) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t bar[TMA_NST], ebar[TMA_NST];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
+  const int i0 = blockIdx.x * TMA_TX + 1, j0 = blockIdx.y * TMA_TY + 1;
+  const int I0 = i0 + g.Hx - 1, J0 = j0 + g.Hy - 1;
+  const int PX = g.PX, n2 = g.n2, Nz = g.Nz;
+  const float eps = g.eps;
+  constexpr int STAGE = DIR == 0 ? GU_STAGE : GV_STAGE;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TMA_NST; s++) { mbar_init(&bar[s], 1); mbar_init(&ebar[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (ty >= TMA_TY) {   // ===== producer warp
+    if (tid == 128)
+      for (int k = 1; k <= Nz; k++) {
+        const int s = (k - 1) % TMA_NST;
+        if (k > TMA_NST) mbar_wait(&ebar[s], (((k - 1) / TMA_NST) - 1) & 1);
+        float* sm = smem + s * STAGE;
+        const int K = k + g.Hz - 1;
+        mbar_expect_tx(&bar[s], STAGE * sizeof(float));
+        if (DIR == 0) {
+          tma_load_3d(sm + GU_OFF_U, &tm.m[0], &bar[s], I0 - 4, J0 - 4, K);
+          tma_load_3d(sm + GU_OFF_V, &tm.m[1], &bar[s], I0 - 4, J0 - 4, K);
+          tma_load_3d(sm + GU_OFF_Z, &tm.m[2], &bar[s], I0, J0 - 4, K);
+          tma_load_3d(sm + GU_OFF_DX, &tm.m[3], &bar[s], I0 - 4, J0, K);
+          tma_load_3d(sm + GU_OFF_DY, &tm.m[4], &bar[s], I0 - 4, J0, K);
+          tma_load_3d(sm + GU_OFF_W, &tm.m[5], &bar[s], I0 - 4, J0, K + 1);
+          tma_load_3d(sm + GU_OFF_P, &tm.m[6], &bar[s], I0 - 4, J0, K);
+        } else {
+          tma_load_3d(sm + GV_OFF_V, &tm.m[0], &bar[s], I0 - 4, J0 - 4, K);
+          tma_load_3d(sm + GV_OFF_U, &tm.m[1], &bar[s], I0 - 4, J0 - 4, K);
+          tma_load_3d(sm + GV_OFF_Z, &tm.m[2], &bar[s], I0 - 4, J0, K);
+          tma_load_3d(sm + GV_OFF_DY, &tm.m[3], &bar[s], I0, J0 - 4, K);
+          tma_load_3d(sm + GV_OFF_DX, &tm.m[4], &bar[s], I0, J0 - 4, K);
+          tma_load_3d(sm + GV_OFF_W, &tm.m[5], &bar[s], I0, J0 - 4, K + 1);
+          tma_load_3d(sm + GV_OFF_P, &tm.m[6], &bar[s], I0, J0 - 4, K);
+        }
+      }
+    return;
+  }
+  const int lx = 2 * tx;
+  const int i = min(i0 + lx, g.Nx - 1), j = min(j0 + ty, g.Ny);
+  const bool valid = (i0 + lx + 1) <= g.Nx && (j0 + ty) <= g.Ny;
+  const int q2 = id2(g, i, j);
+  // ---- hoisted 2-D data (pairs over the two cells c = 0, 1)
+  float2 rm1, rAz, fbar, mA0, mA1, mB0, mB1, azp[4];
+  int kbA, kbB;
+  if (DIR == 0) {
+    rm1 = make_float2(1.f / g.dxfc[q2], 1.f / g.dxfc[q2 + 1]);
+    rAz = make_float2(1.f / g.azfc[q2], 1.f / g.azfc[q2 + 1]);
+    fbar = make_float2((g.fff[q2] + g.fff[q2 + PX]) * 0.5f, (g.fff[q2 + 1] + g.fff[q2 + 1 + PX]) * 0.5f);
+    mA0 = make_float2(g.dxcf[q2 - 1], g.dxcf[q2]); mA1 = make_float2(g.dxcf[q2 - 1 + PX], g.dxcf[q2 + PX]);        // v at i-1: rows j, j+1
+    mB0 = make_float2(g.dxcf[q2], g.dxcf[q2 + 1]); mB1 = make_float2(g.dxcf[q2 + PX], g.dxcf[q2 + 1 + PX]);        // v at i
+#pragma unroll
+    for (int n = 0; n < 4; n++) azp[n] = make_float2(g.azcc[q2 - 2 + n], g.azcc[q2 - 1 + n]);
+  } else {
+    rm1 = make_float2(1.f / g.dycf[q2], 1.f / g.dycf[q2 + 1]);
+    rAz = make_float2(1.f / g.azcf[q2], 1.f / g.azcf[q2 + 1]);
+    fbar = make_float2((g.fff[q2] + g.fff[q2 + 1]) * 0.5f, (g.fff[q2 + 1] + g.fff[q2 + 2]) * 0.5f);
+    mA0 = make_float2(g.dyfc[q2 - PX], g.dyfc[q2 - PX + 1]); mA1 = make_float2(g.dyfc[q2 - PX + 1], g.dyfc[q2 - PX + 2]);  // u at j-1: cols i, i+1
+    mB0 = make_float2(g.dyfc[q2], g.dyfc[q2 + 1]); mB1 = make_float2(g.dyfc[q2 + 1], g.dyfc[q2 + 2]);                      // u at j
+#pragma unroll
+    for (int n = 0; n < 4; n++) azp[n] = make_float2(g.azcc[q2 + (n - 2) * PX], g.azcc[q2 + (n - 2) * PX + 1]);
+  }
+  kbA = g.kb[q2]; kbB = g.kb[q2 + 1];
+  const int kgen = g.kgen2[q2], kzero = g.kzero2[q2];   // pair-based (identical for both cells)
+  // ---- vertical register windows of the own velocity
+  size_t q3 = q2 + (size_t)n2 * g.Hz;
+  float WA[7], WB[7];
+#pragma unroll
+  for (int m = 0; m < 7; m++) {
+    const float2 a = __ldg(reinterpret_cast<const float2*>(own_g + q3 + (ptrdiff_t)(m - 3) * n2));
+    WA[m] = a.x; WB[m] = a.y;
+  }
+  float2 Wb = make_float2(0.f, 0.f);
+  for (int k = 1; k <= Nz; k++, q3 += n2) {
+    const int s = (k - 1) % TMA_NST;
+    mbar_wait(&bar[s], ((k - 1) / TMA_NST) & 1);
+    const float* sm = smem + s * STAGE;
+    float2 out = make_float2(0.f, 0.f);
+    bool store = false;
+    if (valid) {
+      if (k <= kzero) { Wb = make_float2(0.f, 0.f); store = true; }
+      else if (k > kgen) {
+        store = true;
+        if (k == kgen + 1 && kgen > 0) Wb = make_float2(carry[q2], carry[q2 + 1]);
+        const float dz = g.dzc[k + g.Hz - 1];
+        const float2 own0 = make_float2(WA[3], WB[3]);
+        const bool lA = own0.x > 0.f, lB = own0.y > 0.f;
+        const int Bw = (g.immersed && k + 1 > Nz) ? 1 : 2;
+        float2 Hterm, Phi, Bsum, wt, oavg, dpp;
+        if (DIR == 0) {
+          const float* U = sm + GU_OFF_U + (ty + 4) * GU_PU + (lx + 4); const float* V = sm + GU_OFF_V + (ty + 4) * GU_PV + (lx + 4);
+          const float* Z = sm + GU_OFF_Z + (ty + 4) * GU_PZ + lx; const float* DX = sm + GU_OFF_DX + ty * GU_PD + (lx + 4);
+          const float* DY = sm + GU_OFF_DY + ty * GU_PD + (lx + 4); const float* W = sm + GU_OFF_W + ty * GU_PD + (lx + 4);
+          const float* P = sm + GU_OFF_P + ty * GU_PP + (lx + 4);
+          // rows j-3 .. j+3 of u at the pair, rows j-2 .. j+3 of v at (i-1, i) and (i, i+1), of zeta at the pair
+          float2 uy[7], vw[6], ve[6], zq[6], zs[6], zr[6];
+#pragma unroll
+          for (int m = 0; m < 7; m++) uy[m] = ldpa(U + (m - 3) * GU_PU);
+#pragma unroll
+          for (int m = 0; m < 6; m++) {
+            vw[m] = ldp(V + (m - 2) * GU_PV - 1); ve[m] = ldpa(V + (m - 2) * GU_PV);
+            zq[m] = ldpa(Z + (m - 2) * GU_PZ);
+            zs[m] = pmuls(padd(uy[m], uy[m + 1]), 0.5f);
+            zr[m] = pmuls(padd(vw[m], ve[m]), 0.5f);
+          }
+          const float2 xm0 = pmul(mA0, vw[2]), xm1 = pmul(mA1, vw[3]), x00 = pmul(mB0, ve[2]), x01 = pmul(mB1, ve[3]);
+          oavg = pmuls(padd(pmuls(padd(xm0, xm1), 0.5f), pmuls(padd(x00, x01), 0.5f)), 0.5f);
+          const float2 ohat = pmul(oavg, rm1);
+          Hterm = pneg(pmul(ohat, pweno5_vs_sel(zq, zs, zr, ohat.x > 0.f, ohat.y > 0.f, eps)));
+          // x windows: cells i-3 .. i+3
+          float2 ux[7], dOw[6], dv[6], dK[6], sK[6], hs[7], dyx[6];
+#pragma unroll
+          for (int n = 0; n < 7; n++) { ux[n] = (n & 1) ? ldpa(U + n - 3 + 0) : ldp(U + n - 3); }
+#pragma unroll
+          for (int n = 0; n < 7; n++) hs[n] = pmuls(pmul(ux[n], ux[n]), 0.5f);
+#pragma unroll
+          for (int m = 0; m < 6; m++) {
+            dOw[m] = (m & 1) ? ldpa(DX + m - 3) : ldp(DX + m - 3);
+            dyx[m] = (m & 1) ? ldpa(DY + m - 3) : ldp(DY + m - 3);
+            dv[m] = padd(dOw[m], dyx[m]);
+            dK[m] = psub(hs[m + 1], hs[m]);
+            sK[m] = pmuls(padd(ux[m], ux[m + 1]), 0.5f);
+          }
+          const float2 dvs = psym4(dyx[1], dyx[2], dyx[3], dyx[4], 2);
+          Phi = pmul(own0, padd(dvs, pweno5_fs_sel(dOw, dv, lA, lB, eps)));
+          const float2 dKo = pweno5_fs_sel(dK, sK, lA, lB, eps);
+          float2 kc[4];
+#pragma unroll
+          for (int m = 0; m < 4; m++) kc[m] = psub(pmuls(pmul(ve[m + 1], ve[m + 1]), 0.5f), pmuls(pmul(vw[m + 1], vw[m + 1]), 0.5f));
+          Bsum = padd(dKo, psym4(kc[0], kc[1], kc[2], kc[3], 2));
+          wt = psym4(pmul(azp[0], ldpa(W - 2)), pmul(azp[1], ldp(W - 1)), pmul(azp[2], ldpa(W)), pmul(azp[3], ldp(W + 1)), Bw);
+          dpp = psub(ldpa(P), ldp(P - 1));
+        } else {
+          const float* V = sm + GV_OFF_V + (ty + 4) * GV_PV + (lx + 4); const float* U = sm + GV_OFF_U + (ty + 4) * GV_PU + (lx + 4);
+          const float* Z = sm + GV_OFF_Z + ty * GV_PZ + (lx + 4); const float* DY = sm + GV_OFF_DY + (ty + 4) * GV_PD + lx;
+          const float* DX = sm + GV_OFF_DX + (ty + 4) * GV_PD + lx; const float* W = sm + GV_OFF_W + (ty + 4) * GV_PD + lx;
+          const float* P = sm + GV_OFF_P + (ty + 4) * GV_PD + lx;
+          // x windows (cols i-2 .. i+3): zeta, v row j (cols i-3 .. i+3), u rows j-1 and j
+          float2 vx[7], us[6], un[6], zq[6], zs[6], zr[6];
+#pragma unroll
+          for (int n = 0; n < 7; n++) vx[n] = (n & 1) ? ldpa(V + n - 3) : ldp(V + n - 3);
+#pragma unroll
+          for (int m = 0; m < 6; m++) {
+            us[m] = (m & 1) ? ldp(U - GV_PU + m - 2) : ldpa(U - GV_PU + m - 2);
+            un[m] = (m & 1) ? ldp(U + m - 2) : ldpa(U + m - 2);
+            zq[m] = (m & 1) ? ldp(Z + m - 2) : ldpa(Z + m - 2);
+            zs[m] = pmuls(padd(vx[m], vx[m + 1]), 0.5f);
+            zr[m] = pmuls(padd(us[m], un[m]), 0.5f);
+          }
+          const float2 xm0 = pmul(mA0, us[2]), xm1 = pmul(mA1, us[3]), x00 = pmul(mB0, un[2]), x01 = pmul(mB1, un[3]);
+          oavg = pmuls(padd(pmuls(padd(xm0, xm1), 0.5f), pmuls(padd(x00, x01), 0.5f)), 0.5f);
+          const float2 ohat = pmul(oavg, rm1);
+          Hterm = pmul(ohat, pweno5_vs_sel(zq, zs, zr, ohat.x > 0.f, ohat.y > 0.f, eps));
+          // y windows: rows j-3 .. j+3
+          float2 vy[7], dOw[6], dv[6], dK[6], sK[6], hs[7], dxy[6];
+#pragma unroll
+          for (int n = 0; n < 7; n++) { vy[n] = ldpa(V + (n - 3) * GV_PV); hs[n] = pmuls(pmul(vy[n], vy[n]), 0.5f); }
+#pragma unroll
+          for (int m = 0; m < 6; m++) {
+            dOw[m] = ldpa(DY + (m - 3) * GV_PD);
+            dxy[m] = ldpa(DX + (m - 3) * GV_PD);
+            dv[m] = padd(dxy[m], dOw[m]);
+            dK[m] = psub(hs[m + 1], hs[m]);
+            sK[m] = pmuls(padd(vy[m], vy[m + 1]), 0.5f);
+          }
+          const float2 dus = psym4(dxy[1], dxy[2], dxy[3], dxy[4], 2);
+          Phi = pmul(own0, padd(dus, pweno5_fs_sel(dOw, dv, lA, lB, eps)));
+          const float2 dKo = pweno5_fs_sel(dK, sK, lA, lB, eps);
+          float2 kc[4];
+#pragma unroll
+          for (int m = 0; m < 4; m++) kc[m] = psub(pmuls(pmul(un[m + 1], un[m + 1]), 0.5f), pmuls(pmul(us[m + 1], us[m + 1]), 0.5f));
+          Bsum = padd(dKo, psym4(kc[0], kc[1], kc[2], kc[3], 2));
+          wt = psym4(pmul(azp[0], ldpa(W - 2 * GV_PD)), pmul(azp[1], ldpa(W - GV_PD)), pmul(azp[2], ldpa(W)), pmul(azp[3], ldpa(W + GV_PD)), Bw);
+          dpp = psub(ldpa(P), ldpa(P - GV_PD));
+        }
+        const float2 Wt = pmul(wt, pvert(WA, WB, zbuf(g, kbA, k + 1, 3), zbuf(g, kbB, k + 1, 3), wt, eps));
+        const float2 Vterm = pmul(pmuls(rAz, 1.f / dz), padd(Phi, psub(Wt, Wb)));
+        Wb = Wt;
+        const float2 ct = pmul(pmul(fbar, oavg), rm1);          // Gu: -(-ct) ; Gv: -(+ct)
+        const float2 sum = padd(padd(Hterm, Vterm), pmul(Bsum, rm1));
+        const float2 rest = padd(DIR == 0 ? pneg(ct) : ct, pmul(dpp, rm1));
+        out = pneg(padd(sum, rest));
+      }
+      if (store) *reinterpret_cast<float2*>(G + q3) = out;
+      const float2 a = __ldg(reinterpret_cast<const float2*>(own_g + q3 + (size_t)4 * n2));
+#pragma unroll
+      for (int m = 0; m < 6; m++) { WA[m] = WA[m + 1]; WB[m] = WB[m + 1]; }
+      WA[6] = a.x; WB[6] = a.y;
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&ebar[s]);
+  }
+}
+
+// =====================================================================================
 // Tracer tendencies (row A6), TMA-staged.  CTA = 32 x 16 columns; 128 consumer threads, each owning a 2 x 2 patch
 // of columns so that the x- and y-face fluxes inside the patch are computed once (16 reconstructions for 4 cells:
 // 4.0 per cell instead of 4.5 in the register-blocked kernel and 6 in the per-cell one); one tracer per blockIdx.z.
@@ -596,6 +836,8 @@ static TmaState* tma_state(Handle* h) {
   ok &= make_map(g, h->f.w, TR_TX, TR_TY, &t->tr.m[4]);
   if (ok) {
     ok &= cudaFuncSetAttribute(k_tracer_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * TR_STAGE * (int)sizeof(float)) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(k_mom_tma_p2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GU_STAGE * (int)sizeof(float)) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(k_mom_tma_p2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GV_STAGE * (int)sizeof(float)) == cudaSuccess;
     ok &= cudaFuncSetAttribute(k_gu_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GU_STAGE * (int)sizeof(float)) == cudaSuccess;
     ok &= cudaFuncSetAttribute(k_gv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GV_STAGE * (int)sizeof(float)) == cudaSuccess;
   }
@@ -608,6 +850,16 @@ void tma_free(Handle* h) { delete (TmaState*)h->tma; h->tma = nullptr; }
 void launch_momentum_tendency_tma(Handle* h) {
   TmaState* t = tma_state(h);
   const DevGrid& g = h->g;
+  if (h->use_packed) {
+    dim3 b(16, TMA_TY + 2), gr((g.Nx + TMA_TX - 1) / TMA_TX, (g.Ny + TMA_TY - 1) / TMA_TY);
+    { StageScope ts(h, "kernel:k_gu_tma");
+      k_mom_tma_p2<0><<<gr, b, TMA_NST * GU_STAGE * sizeof(float), h->stream>>>(g, t->gu, h->f.u, h->f.gn[0], h->carry[0]); }
+    h->count_launch();
+    { StageScope ts(h, "kernel:k_gv_tma");
+      k_mom_tma_p2<1><<<gr, b, TMA_NST * GV_STAGE * sizeof(float), h->stream>>>(g, t->gv, h->f.v, h->f.gn[1], h->carry[1]); }
+    h->count_launch();
+    return;
+  }
   dim3 b(TMA_TX, TMA_TY + 1), gr((g.Nx + TMA_TX - 1) / TMA_TX, (g.Ny + TMA_TY - 1) / TMA_TY);
   { StageScope ts(h, "kernel:k_gu_tma");
   k_gu_tma<<<gr, b, TMA_NST * GU_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gu, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[0], h->carry[0]); }
