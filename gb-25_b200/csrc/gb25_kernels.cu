@@ -193,6 +193,7 @@ __global__ void k_compute_p(DevGrid g, const float* __restrict__ T, const float*
   const float gr = g.g, r0 = g.rho0;
   float bup = -(gr * teos10_rho_prime(T[q3], S[q3], g.zc[g.Nz + 1 + g.Hz - 1], r0, g.eos_r0) / r0);
   float pk = 0.f;
+#pragma unroll 4
   for (int k = g.Nz; k >= 1; k--) {
     q3 -= g.n2;
     const float b = -(gr * teos10_rho_prime(T[q3], S[q3], g.zc[k + g.Hz - 1], r0, g.eos_r0) / r0);
@@ -432,7 +433,7 @@ __global__ void k_ab2_fused(DevGrid g, DevFields f, float* __restrict__ us2, flo
   const bool imm = g.immersed;
   float su = 0.f, sv = 0.f, bu = 0.f, bv = 0.f;
   size_t q3 = q2 + (size_t)n2 * g.Hz;
-  for (int k = 1; k <= g.Nz; k++, q3 += n2) {
+  for (int k = 1; k <= g.Nz; k++, q3 += n2) {   // (unrolling this loop costs occupancy: 0.54 -> 0.68 ms, measured)
     const float dz = g.dzc[k + g.Hz - 1];
     const float gu = c1 * f.gn[0][q3] - c2 * f.gm[0][q3] * ne;
     const float gv = c1 * f.gn[1][q3] - c2 * f.gm[1][q3] * ne;
@@ -468,6 +469,7 @@ __global__ void k_correct_fused(DevGrid g, DevFields f, const float* __restrict_
   const bool ywall = y_outside(g, j) || y_outside(g, j - 1);
   const bool imm = g.immersed;
   size_t q3 = q2 + (size_t)n2 * g.Hz;
+#pragma unroll 4
   for (int k = 1; k <= g.Nz; k++, q3 += n2) {
     float un = f.u[q3] + cu, vn = f.v[q3] + cv;
     if (imm) {

@@ -199,6 +199,9 @@ __global__ void __launch_bounds__(128) k_aux_columns(DevGrid g, const float* __r
   size_t q3 = q2 + (size_t)n2 * g.Hz;  // k = 1
   float wk = 0.f;
   w[q3] = 0.f;
+  const float raz = 1.f;   // (divisions stay IEEE: w and zeta are compared element-wise)
+  (void)raz;
+#pragma unroll 4
   for (int k = 1; k <= g.Nz; k++, q3 += n2) {
     const float dz = g.dzc[k + g.Hz - 1];
     const float u0 = u[q3], v0 = v[q3];
