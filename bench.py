@@ -41,6 +41,7 @@ ALGORITHMIC_BYTES_PER_CELL_STEP = 104     # 26 Float32 words o
 # algorithmic bytes per cell of one launch of each tendency kernel (DESIGN.md "kernels")
 # ("kernel:<name>" entries are single-launch CUDA-event timers of libgb25cuda)
 KERNEL_BYTES_PER_CELL = {"kernel:k_tracer_tendency_v2": (5 + 2) * 4,   # one launch, both tracers: read u,v,w,T,S, write GT,GS
+                         "kernel:k_tracer_tma": (5 + 2) * 4,
                          "kernel:k_gu_tma": (4 + 1) * 4,                # read u,v,w,p, write Gu
                          "kernel:k_gv_tma": (4 + 1) * 4,
                          "kernel:k_ab2_fused": 16 * 4,                  # read 4 fields + 8 G, write 4 fields
@@ -48,7 +49,9 @@ KERNEL_BYTES_PER_CELL = {"kernel:k_tracer_tendency_v2": (5 + 2) * 4,   # one lau
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` captures under
 # profiles/ (tripolar 1440x600x50 workload); None = not captured for this kernel version
 NCU_TRAFFIC_BYTES = {"kernel:k_tracer_tendency_v2": 1459761000 + 330897408,   # profiles/ncu_r1_v3_top_kernels.md
-                     "kernel:k_gu_tma": 1327310000 + 169361408, "kernel:k_gv_tma": 1404815000 + 168233728}
+                     # profiles/ncu_r1_v4_top_kernels.md (TMA + packed-FP32x2 kernels)
+                     "kernel:k_tracer_tma": 1514392000 + 332068096, "kernel:k_gu_tma": 1320836000 + 165283072,
+                     "kernel:k_gv_tma": 1384651000 + 168194560}
 
 
 def measured_peaks():
