@@ -17,6 +17,9 @@
 //     in both directions, so a tile can only re-write a neighbour's halo after it has received something the
 //     neighbour sent after consuming the previous contents.
 #include <cstring>
+#include <cstdlib>
+
+#include <cuda.h>   // CUstream / CUdeviceptr types; entry points come from cudaGetDriverEntryPoint
 
 #include "gb25_internal.h"
 
@@ -106,19 +109,58 @@ static PushBatch make_push(Handle* h, const HaloSpec* specs, int n, int slot, bo
   }
   return pb;
 }
+// Stream memory operations: the flag write / wait is executed by the GPU front end in stream order (no kernel
+// launch, no SM).  The write carries the default memory barrier, so the peer stores of the preceding push kernel
+// are visible at the destination before the flag.  GB25_STREAM_MEMOPS=0 (or a driver without the entry points)
+// falls back to the one-warp signal / wait kernels, whose wait has a time-out.
+typedef CUresult (*PFN_writeValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*PFN_waitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static PFN_writeValue32 g_write32 = nullptr;
+static PFN_waitValue32 g_wait32 = nullptr;
+static int g_memops = -1;
+static bool memops_available() {
+  if (g_memops < 0) {
+    g_memops = 0;
+    const char* e = getenv("GB25_STREAM_MEMOPS");
+    if (!(e && e[0] == '0')) {
+      void *pw = nullptr, *pq = nullptr;
+      cudaDriverEntryPointQueryResult q1, q2;
+      if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &pw, cudaEnableDefault, &q1) == cudaSuccess && q1 == cudaDriverEntryPointSuccess &&
+          cudaGetDriverEntryPoint("cuStreamWaitValue32", &pq, cudaEnableDefault, &q2) == cudaSuccess && q2 == cudaDriverEntryPointSuccess) {
+        g_write32 = (PFN_writeValue32)pw; g_wait32 = (PFN_waitValue32)pq; g_memops = 1;
+      }
+    }
+  }
+  return g_memops == 1;
+}
 static void signal_slots(Handle* h, int slot_mask) {
   Exchange& X = h->ex;
   SignalSet s; s.n = 0;
   for (int sl = 0; sl < EX_NSLOT; sl++)
     if (((slot_mask >> sl) & 1) && X.to[sl].rank >= 0 && X.to[sl].rank != X.rank) s.dst[s.n++] = X.to[sl].flags + kOpposite[sl];
-  if (s.n) { k_signal<<<1, 32, 0, h->stream>>>(s, X.seq); h->count_launch(); }
+  if (!s.n) return;
+  if (memops_available()) {
+    bool ok = true;
+    for (int q = 0; q < s.n; q++) ok &= g_write32((CUstream)h->stream, (CUdeviceptr)s.dst[q], (cuuint32_t)X.seq, CU_STREAM_WRITE_VALUE_DEFAULT) == CUDA_SUCCESS;
+    if (ok) return;
+    g_memops = 0;   // (not supported on this address / driver: use the kernels from now on)
+  }
+  k_signal<<<1, 32, 0, h->stream>>>(s, X.seq); h->count_launch();
 }
 static void wait_slots(Handle* h, int slot_mask) {
   Exchange& X = h->ex;
   int m = 0;
   for (int sl = 0; sl < EX_NSLOT; sl++)
     if (((slot_mask >> sl) & 1) && X.to[sl].rank >= 0 && X.to[sl].rank != X.rank) m |= 1 << sl;
-  if (m) { k_wait<<<1, 32, 0, h->stream>>>(X.flags, m, X.seq); h->count_launch(); }
+  if (!m) return;
+  if (memops_available()) {
+    bool ok = true;
+    for (int sl = 0; sl < EX_NSLOT; sl++)
+      if ((m >> sl) & 1) ok &= g_wait32((CUstream)h->stream, (CUdeviceptr)(X.flags + sl), (cuuint32_t)X.seq, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS;
+    if (ok) return;
+    g_memops = 0;
+  }
+  k_wait<<<1, 32, 0, h->stream>>>(X.flags, m, X.seq); h->count_launch();
 }
 
 void launch_fill_halo_dist(Handle* h, const HaloSpec* specs, int n, bool three_d) {
