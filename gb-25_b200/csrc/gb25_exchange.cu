@@ -217,51 +217,25 @@ void launch_fill_halo_dist(Handle* h, const HaloSpec* specs, int n, bool three_d
   }
 }
 
-// one-cell refresh of the barotropic halos between the substep kernels (no corners involved)
+// one-cell refresh of the barotropic halos between the substep kernels (no corners involved): the substep kernels
+// push their edges themselves (BaroPeers in gb25_kernels.cu); here only the flags are published and awaited
 void exchange_baro_eta(Handle* h) {   // after the eta kernel: the U,V kernel reads eta(i-1), eta(j-1)
   Exchange& X = h->ex;
-  const DevGrid& g = h->g; const gb25_config& c = h->cfg;
-  HaloSpec s[1] = {{h->f.eta, 0, 0, 1, 1.f}};
+  const gb25_config& c = h->cfg;
   int mask_out = 0, mask_in = 0;
-  if (c.Rx > 1) {
-    PushBatch pb = make_push(h, s, 1, SLOT_E);
-    dim3 bc(1, 128), gc((g.Ny + 127) / 128, 1, 1);
-    k_push_cols<<<gc, bc, 0, h->stream>>>(g, pb, g.Nx + g.Hx - 1, g.Hx - 1, 1, 0, g.Hy, g.Ny); h->count_launch();   // col Nx -> col 0
-    mask_out |= 1 << SLOT_E; mask_in |= 1 << SLOT_W;
-  }
-  if (c.ry < c.Ry - 1) {
-    PushBatch pb = make_push(h, s, 1, SLOT_N);
-    dim3 b(128), gr((g.Nx + 127) / 128, 1, 1);
-    k_push_rows<<<gr, b, 0, h->stream>>>(g, pb, g.Ny + g.Hy - 1, g.Hy - 1, 1, 0, 1, 0); h->count_launch();          // row Ny -> row 0
-    mask_out |= 1 << SLOT_N;
-  }
+  if (c.Rx > 1) { mask_out |= 1 << SLOT_E; mask_in |= 1 << SLOT_W; }
+  if (c.ry < c.Ry - 1) mask_out |= 1 << SLOT_N;
   if (c.ry > 0) mask_in |= 1 << SLOT_S;
   if (mask_out | mask_in) { X.seq++; signal_slots(h, mask_out); wait_slots(h, mask_in); }
 }
 void exchange_baro_uv(Handle* h) {    // after the U,V kernel: the eta kernel reads U(i+1), V(j+1)
   Exchange& X = h->ex;
-  const DevGrid& g = h->g; const gb25_config& c = h->cfg;
-  HaloSpec su[1] = {{h->f.bu, 1, 0, 0, -1.f}}, sv[1] = {{h->f.bv, 0, 1, 0, -1.f}};
+  const gb25_config& c = h->cfg;
   int mask_out = 0, mask_in = 0;
-  if (c.Rx > 1) {
-    PushBatch pb = make_push(h, su, 1, SLOT_W);
-    dim3 bc(1, 128), gc((g.Ny + 127) / 128, 1, 1);
-    k_push_cols<<<gc, bc, 0, h->stream>>>(g, pb, g.Hx, g.Nx + g.Hx, 1, 0, g.Hy, g.Ny); h->count_launch();           // col 1 -> col Nx+1
-    mask_out |= 1 << SLOT_W; mask_in |= 1 << SLOT_E;
-  }
-  if (c.ry > 0) {
-    PushBatch pb = make_push(h, sv, 1, SLOT_S);
-    dim3 b(128), gr((g.Nx + 127) / 128, 1, 1);
-    k_push_rows<<<gr, b, 0, h->stream>>>(g, pb, g.Hy, g.Ny + g.Hy, 1, 0, 1, 0); h->count_launch();                   // row 1 -> row Ny+1
-    mask_out |= 1 << SLOT_S;
-  }
+  if (c.Rx > 1) { mask_out |= 1 << SLOT_W; mask_in |= 1 << SLOT_E; }
+  if (c.ry > 0) mask_out |= 1 << SLOT_S;
   if (c.ry < c.Ry - 1) mask_in |= 1 << SLOT_N;
-  if (c.topo_y == GB25_TOPO_FOLD && c.ry == c.Ry - 1 && c.Rx > 1) {
-    PushBatch pb = make_push(h, sv, 1, SLOT_FOLD);
-    dim3 b(128), gr((g.Nx + 127) / 128, 1, 1);
-    k_push_fold<<<gr, b, 0, h->stream>>>(g, pb, 0, 1, 0, 0); h->count_launch();                                     // V(i, Ny+1) = -V(Nx-i+1, Ny)
-    mask_out |= 1 << SLOT_FOLD; mask_in |= 1 << SLOT_FOLD;
-  }
+  if (c.topo_y == GB25_TOPO_FOLD && c.ry == c.Ry - 1 && c.Rx > 1) { mask_out |= 1 << SLOT_FOLD; mask_in |= 1 << SLOT_FOLD; }
   if (mask_out | mask_in) { X.seq++; signal_slots(h, mask_out); wait_slots(h, mask_in); }
 }
 

@@ -303,7 +303,11 @@ void launch_ab2_columns(Handle* h, float dt, float chi) {
 // Edge handling: a tile that spans the whole direction applies the topology itself (periodic wrap, wall, fold);
 // on a partitioned grid the one-cell halos of eta / U / V are refreshed by the neighbours after every kernel.
 //   bflags bit 0: wrap in x locally (Rx == 1); bit 1: south wall; bit 2: north wall; bit 3: local north fold
-__global__ void k_baro_eta(DevGrid g, float* __restrict__ eta, const float* __restrict__ U, const float* __restrict__ V, float dtau, int bflags) {
+// On a partitioned grid the kernels also PUSH their edge values straight into the neighbours' one-cell halos
+// (peer stores over NVLink from the threads that own the edge): no separate copy kernels between the substeps.
+struct BaroPeers { float *eta_E, *eta_N, *bu_W, *bv_S, *bv_F; };
+__global__ void k_baro_eta(DevGrid g, float* __restrict__ eta, const float* __restrict__ U, const float* __restrict__ V, float dtau, int bflags,
+                           BaroPeers pe) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
   if (i > g.Nx) return;
   const int q2 = id2(g, i, j), PX = g.PX;
@@ -318,9 +322,12 @@ __global__ void k_baro_eta(DevGrid g, float* __restrict__ eta, const float* __re
       dV = g.dxcf[q2 + PX] * vn - g.dxcf[q2] * V[q2];
     }
   } else dV = g.dxcf[q2 + PX] * V[q2 + PX] - g.dxcf[q2] * V[q2];
-  eta[q2] -= dtau * (dU + dV) / g.azcc[q2];
+  const float en = eta[q2] - dtau * (dU + dV) / g.azcc[q2];
+  eta[q2] = en;
+  if (pe.eta_E && i == g.Nx) pe.eta_E[id2(g, 0, j)] = en;          // my last column  -> the east tile's west halo
+  if (pe.eta_N && j == g.Ny) pe.eta_N[id2(g, i, 0)] = en;          // my last row     -> the north tile's south halo
 }
-__global__ void k_baro_uv(DevGrid g, DevFields f, float dtau, float wgt, int bflags) {
+__global__ void k_baro_uv(DevGrid g, DevFields f, float dtau, float wgt, int bflags, BaroPeers pe) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
   if (i > g.Nx) return;
   const int q2 = id2(g, i, j);
@@ -331,6 +338,9 @@ __global__ void k_baro_uv(DevGrid g, DevFields f, float dtau, float wgt, int bfl
   const float Un = f.bu[q2] + dtau * (-g.g * g.Hfc[q2] * dxe + f.gU[q2]);
   const float Vn = f.bv[q2] + dtau * (-g.g * g.Hcf[q2] * dye + f.gV[q2]);
   f.bu[q2] = Un; f.bv[q2] = Vn;
+  if (pe.bu_W && i == 1) pe.bu_W[id2(g, g.Nx + 1, j)] = Un;                       // my first column -> the west tile's east halo
+  if (pe.bv_S && j == 1) pe.bv_S[id2(g, i, g.Ny + 1)] = Vn;                       // my first row    -> the south tile's north halo
+  if (pe.bv_F && j == g.Ny) pe.bv_F[id2(g, g.Nx - i + 1, g.Ny + 1)] = -Vn;        // fold: V(i', Ny+1) = -V(Nx-i'+1, Ny) on the partner
   f.feta[q2] += wgt * e0;
   f.fu[q2] += wgt * Un;
   f.fv[q2] += wgt * Vn;
@@ -352,10 +362,18 @@ void launch_barotropic(Handle* h, float dt) {
   const gb25_config& c = h->cfg;
   const int bflags = (c.Rx == 1 ? 1 : 0) | (c.ry == 0 ? 2 : 0) | ((c.ry == c.Ry - 1 && c.topo_y == GB25_TOPO_BOUNDED) ? 4 : 0) |
                      ((c.ry == c.Ry - 1 && c.topo_y == GB25_TOPO_FOLD && c.Rx == 1) ? 8 : 0);
+  BaroPeers pe = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (h->ex.on) {
+    const Exchange& X = h->ex;
+    if (c.Rx > 1) { pe.eta_E = X.to[SLOT_E].fld[EX_ETA]; pe.bu_W = X.to[SLOT_W].fld[EX_BU]; }
+    if (c.ry < c.Ry - 1) pe.eta_N = X.to[SLOT_N].fld[EX_ETA];
+    if (c.ry > 0) pe.bv_S = X.to[SLOT_S].fld[EX_BV];
+    if (c.topo_y == GB25_TOPO_FOLD && c.ry == c.Ry - 1 && c.Rx > 1) pe.bv_F = X.to[SLOT_FOLD].fld[EX_BV];
+  }
   for (int m = 0; m < h->cfg.nsubsteps; m++) {
-    k_baro_eta<<<gr, b, 0, h->stream>>>(g, h->f.eta, h->f.bu, h->f.bv, dtau, bflags); h->count_launch();
+    k_baro_eta<<<gr, b, 0, h->stream>>>(g, h->f.eta, h->f.bu, h->f.bv, dtau, bflags, pe); h->count_launch();
     if (h->ex.on) exchange_baro_eta(h);
-    k_baro_uv<<<gr, b, 0, h->stream>>>(g, h->f, dtau, h->weights[m], bflags); h->count_launch();
+    k_baro_uv<<<gr, b, 0, h->stream>>>(g, h->f, dtau, h->weights[m], bflags, pe); h->count_launch();
     if (h->ex.on) exchange_baro_uv(h);
   }
   k_baro_finish<<<gr, b, 0, h->stream>>>(g, h->f); h->count_launch();
