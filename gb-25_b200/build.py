@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libgb25cuda.so")
-CU_SOURCES = ["gb25_api.cu", "gb25_kernels.cu", "gb25_tend_v2.cu", "gb25_tend_tma.cu", "gb25_exchange.cu"]
+CU_SOURCES = ["gb25_api.cu", "gb25_kernels.cu", "gb25_tend_v2.cu", "gb25_tend_tma.cu", "gb25_exchange.cu", "gb25_baro.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -201,6 +201,7 @@ extern "C" int gb25_destroy(gb25_handle* h) {
   if (h->graph) cudaGraphDestroy(h->graph);
   exchange_close(h);
   tma_free(h);
+  baro_plan_free(h);
   for (void* p : h->allocs) cudaFree(p);
   if (h->stage_dev) cudaFree(h->stage_dev);
   for (auto& s : h->timers) for (auto& e : s.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -323,6 +324,8 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     h->use_packed = !(pk && pk[0] == '0');
     const char* tt = getenv("GB25_TMA_TRACER");
     h->use_tma_tracer = !(tt && tt[0] == '0');
+    const char* bp = getenv("GB25_BARO_PERSISTENT");
+    h->use_baro_persistent = !(bp && bp[0] == '0');
   }
   DevFields& f = h->f;
   f.u = h->field_ptr[GB25_U]; f.v = h->field_ptr[GB25_V]; f.w = h->field_ptr[GB25_W];
@@ -388,6 +391,7 @@ extern "C" int gb25_synchronize(gb25_handle* h) {
   REQUIRE(h);
   CK(h, cudaStreamSynchronize(h->stream));
   if (exchange_check_timeout(h)) { h->err = "halo exchange timed out waiting for a neighbour tile"; h->sticky = GB25_ERR_COMM; return GB25_ERR_COMM; }
+  if (baro_check_timeout(h)) { h->err = "split-explicit substeps timed out waiting for a neighbouring band or tile"; h->sticky = GB25_ERR_COMM; return GB25_ERR_COMM; }
   return check_async(h, "gb25_synchronize");
 }
 

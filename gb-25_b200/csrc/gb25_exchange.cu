@@ -322,6 +322,7 @@ extern "C" int gb25_exchange_connect(gb25_handle* h, const void* blobs, int nran
   }
   X.seq = 0;
   X.on = true;
+  baro_plan_free(h);   // the persistent substep kernel restarts its sequence numbers on the (zeroed) shared flag buffer
   return GB25_OK;
 }
 

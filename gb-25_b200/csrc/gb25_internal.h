@@ -76,6 +76,8 @@ struct gb25_handle {
   bool use_tma_tracer = true;
   bool use_packed = true;              // FP32x2 (FFMA2) momentum kernels
   void* tma = nullptr;   // TMA tensor maps (gb25_tend_tma.cu)
+  bool use_baro_persistent = true;     // all split-explicit substeps in one persistent kernel (gb25_baro.cu)
+  void* baro_plan = nullptr;   // persistent split-explicit kernel: band decomposition, flags (gb25_baro.cu)
 
   inline void count_launch() { launches++; }
 };
@@ -134,3 +136,6 @@ void launch_correct_fused(Handle* h);
 void launch_vdiff_explicit(Handle* h);
 void launch_implicit_columns(Handle* h, float dt, bool with_sums);
 void launch_barotropic_substeps(Handle* h, float dt);
+bool launch_barotropic_persistent(Handle* h, float dt);   // gb25_baro.cu; false: not applicable, use the substep kernels
+void baro_plan_free(Handle* h);
+int baro_check_timeout(Handle* h);

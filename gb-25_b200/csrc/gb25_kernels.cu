@@ -352,6 +352,7 @@ __global__ void k_baro_finish(DevGrid g, DevFields f) {
   f.eta[q2] = f.feta[q2]; f.bu[q2] = f.fu[q2]; f.bv[q2] = f.fv[q2];
 }
 void launch_barotropic(Handle* h, float dt) {
+  if (launch_barotropic_persistent(h, dt)) return;   // gb25_baro.cu: all substeps in one persistent kernel
   const DevGrid& g = h->g;
   const size_t b2 = (size_t)g.n2 * sizeof(float);
   cudaMemsetAsync(h->f.feta, 0, b2, h->stream);

@@ -231,6 +231,35 @@ def test_tma_kernels_equal_blocked_kernels(oracle_mod, monkeypatch, grid_type, N
     assert M.compare_states(rm_t, rm_b, include_halos=True, rtol=3e-6, atol=0.0, verbose=False, elementwise=1e-5)
 
 
+@pytest.mark.parametrize("grid_type,Nx,Ny,Nz", GRIDS + [("gaussian_islands", 1440, 600, 4), ("simple_lat_lon", 96, 301, 4)])
+@pytest.mark.parametrize("bands", [None, "7"])
+def test_persistent_barotropic_kernel_equals_substep_kernels(monkeypatch, grid_type, Nx, Ny, Nz, bands):
+    """Row A10: the persistent split-explicit kernel (one CTA per SM owning a band of rows, eta/U/V in shared memory,
+    band-to-band flags; gb25_baro.cu) evaluates the expressions of k_baro_eta / k_baro_uv / k_baro_finish
+    (GB25_BARO_PERSISTENT=0): the barotropic state must agree bit for bit, with one row per band, with several
+    rows per band (GB25_BARO_BANDS) and at the benchmark's horizontal size."""
+    if bands:
+        monkeypatch.setenv("GB25_BARO_BANDS", bands)
+    rm_p = M.baroclinic_instability_model(M.B200(0), Nx, Ny, Nz, Δt=60.0, grid_type=grid_type)
+    M.set_baroclinic_instability(rm_p)
+    rng = np.random.default_rng(3)
+    M.set(rm_p, u=1e-3 * rng.random(rm_p.interior("u").shape), v=1e-3 * rng.random(rm_p.interior("v").shape))
+    monkeypatch.setenv("GB25_BARO_PERSISTENT", "0")
+    rm_s = M.baroclinic_instability_model(M.B200(0), Nx, Ny, Nz, Δt=60.0, grid_type=grid_type)
+    monkeypatch.delenv("GB25_BARO_PERSISTENT")
+    M.sync_states(rm_s, rm_p)
+    for m in (rm_p, rm_s):
+        M.first_time_step(m)
+        for _ in range(3):
+            M.time_step(m)
+        m.synchronize()
+    for name in ("eta", "U", "V", "filt_eta", "Gn_U", "Gn_V", "u", "v", "T", "S", "w"):
+        a, b = rm_p.parent(name), rm_s.parent(name)
+        assert np.isfinite(a).all(), name
+        assert np.array_equal(a, b), (name, float(np.abs(a - b).max()))
+    rm_p.close(); rm_s.close()
+
+
 @pytest.mark.parametrize("grid_type,Nx,Ny,Nz", GRIDS)
 @pytest.mark.parametrize("closure", [1, 2])
 def test_vertical_diffusion_closures(oracle_mod, grid_type, Nx, Ny, Nz, closure):
