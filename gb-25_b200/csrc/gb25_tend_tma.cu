@@ -400,6 +400,10 @@ __device__ __forceinline__ float2 pvert(const float (&A)[7], const float (&B)[7]
                      weno_sel_B3(B[1], B[2], B[3], B[4], B[5], B[6], BB, wt.y > 0.f, eps));
 }
 
+// ring depth: measured at 1440 x 600 x 50 (ms per launch pair): 3 stages 1.64, 4 1.63, 5 1.55, 6 1.66 (occupancy drops to 2 CTAs)
+#ifndef MOM_NST
+#define MOM_NST 5
+#endif
 #ifndef MOM_MINB
 #define MOM_MINB 3
 #endif
@@ -408,7 +412,7 @@ __global__ void __launch_bounds__(160, MOM_MINB)
 k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const float* __restrict__ own_g, float* __restrict__ G,
              const float* __restrict__ carry) {
   extern __shared__ __align__(128) float smem[];
-  __shared__ uint64_t bar[TMA_NST], ebar[TMA_NST];
+  __shared__ uint64_t bar[MOM_NST], ebar[MOM_NST];
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
   const int i0 = blockIdx.x * TMA_TX + 1, j0 = blockIdx.y * TMA_TY + 1;
   const int I0 = i0 + g.Hx - 1, J0 = j0 + g.Hy - 1;
@@ -417,15 +421,15 @@ k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const float* __rest
   constexpr int STAGE = DIR == 0 ? GU_STAGE : GV_STAGE;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < TMA_NST; s++) { mbar_init(&bar[s], 1); mbar_init(&ebar[s], 4); }
+    for (int s = 0; s < MOM_NST; s++) { mbar_init(&bar[s], 1); mbar_init(&ebar[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (ty >= TMA_TY) {   // ===== producer warp
     if (tid == 128)
       for (int k = 1; k <= Nz; k++) {
-        const int s = (k - 1) % TMA_NST;
-        if (k > TMA_NST) mbar_wait(&ebar[s], (((k - 1) / TMA_NST) - 1) & 1);
+        const int s = (k - 1) % MOM_NST;
+        if (k > MOM_NST) mbar_wait(&ebar[s], (((k - 1) / MOM_NST) - 1) & 1);
         float* sm = smem + s * STAGE;
         const int K = k + g.Hz - 1;
         mbar_expect_tx(&bar[s], STAGE * sizeof(float));
@@ -485,8 +489,8 @@ k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const float* __rest
   }
   float2 Wb = make_float2(0.f, 0.f);
   for (int k = 1; k <= Nz; k++, q3 += n2) {
-    const int s = (k - 1) % TMA_NST;
-    mbar_wait(&bar[s], ((k - 1) / TMA_NST) & 1);
+    const int s = (k - 1) % MOM_NST;
+    mbar_wait(&bar[s], ((k - 1) / MOM_NST) & 1);
     const float* sm = smem + s * STAGE;
     float2 out = make_float2(0.f, 0.f);
     bool store = false;
@@ -630,6 +634,10 @@ __device__ __forceinline__ float weno5_selp(const float* q, bool left, float eps
   return weno5(v0, v1, v2, v3, v4, eps);
 }
 
+// ring depth (ms per launch): 4 stages 1.08, 5 1.00, 6 1.00
+#ifndef TR_NST
+#define TR_NST 6
+#endif
 #ifndef TR_MINB
 #define TR_MINB 3
 #endif
@@ -637,7 +645,7 @@ __global__ void __launch_bounds__(160, TR_MINB)
 k_tracer_tma(DevGrid g, const __grid_constant__ TmaMaps5 tm, const float* __restrict__ T0, const float* __restrict__ T1,
              float* __restrict__ G0, float* __restrict__ G1, const float* __restrict__ carry0, const float* __restrict__ carry1) {
   extern __shared__ __align__(128) float smem[];
-  __shared__ uint64_t bar[TMA_NST], ebar[TMA_NST];
+  __shared__ uint64_t bar[TR_NST], ebar[TR_NST];
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
   const int i0 = blockIdx.x * TR_TX + 1, j0 = blockIdx.y * TR_TY + 1;
   const int I0 = i0 + g.Hx - 1, J0 = j0 + g.Hy - 1;
@@ -646,15 +654,15 @@ k_tracer_tma(DevGrid g, const __grid_constant__ TmaMaps5 tm, const float* __rest
   const float eps = g.eps;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < TMA_NST; s++) { mbar_init(&bar[s], 1); mbar_init(&ebar[s], TR_CW); }
+    for (int s = 0; s < TR_NST; s++) { mbar_init(&bar[s], 1); mbar_init(&ebar[s], TR_CW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (ty >= 8) {   // ===== producer warp
     if (tid == 128)
       for (int k = 1; k <= Nz; k++) {
-        const int s = (k - 1) % TMA_NST;
-        if (k > TMA_NST) mbar_wait(&ebar[s], (((k - 1) / TMA_NST) - 1) & 1);
+        const int s = (k - 1) % TR_NST;
+        if (k > TR_NST) mbar_wait(&ebar[s], (((k - 1) / TR_NST) - 1) & 1);
         float* sm = smem + s * TR_STAGE;
         const int K = k + g.Hz - 1;
         mbar_expect_tx(&bar[s], TR_STAGE * sizeof(float));
@@ -699,8 +707,8 @@ k_tracer_tma(DevGrid g, const __grid_constant__ TmaMaps5 tm, const float* __rest
   float Fz[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   const int oT = (ly + 4) * TR_PT + (lx + 4), oU = ly * TR_PU + lx, oV = ly * TR_PV + lx;
   for (int k = 1; k <= Nz; k++, q3 += n2) {
-    const int s = (k - 1) % TMA_NST;
-    mbar_wait(&bar[s], ((k - 1) / TMA_NST) & 1);
+    const int s = (k - 1) % TR_NST;
+    mbar_wait(&bar[s], ((k - 1) / TR_NST) & 1);
     const float* sm = smem + s * TR_STAGE;
     const bool fast0 = k > kg[0], fast1 = k > kg[1];
     float out[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
@@ -835,9 +843,9 @@ static TmaState* tma_state(Handle* h) {
   ok &= make_map(g, h->f.v, TR_TX, TR_TY + 1, &t->tr.m[3]);
   ok &= make_map(g, h->f.w, TR_TX, TR_TY, &t->tr.m[4]);
   if (ok) {
-    ok &= cudaFuncSetAttribute(k_tracer_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * TR_STAGE * (int)sizeof(float)) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(k_mom_tma_p2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GU_STAGE * (int)sizeof(float)) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(k_mom_tma_p2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GV_STAGE * (int)sizeof(float)) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(k_tracer_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_NST * TR_STAGE * (int)sizeof(float)) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(k_mom_tma_p2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MOM_NST * GU_STAGE * (int)sizeof(float)) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(k_mom_tma_p2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MOM_NST * GV_STAGE * (int)sizeof(float)) == cudaSuccess;
     ok &= cudaFuncSetAttribute(k_gu_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GU_STAGE * (int)sizeof(float)) == cudaSuccess;
     ok &= cudaFuncSetAttribute(k_gv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GV_STAGE * (int)sizeof(float)) == cudaSuccess;
   }
@@ -853,10 +861,10 @@ void launch_momentum_tendency_tma(Handle* h) {
   if (h->use_packed) {
     dim3 b(16, TMA_TY + 2), gr((g.Nx + TMA_TX - 1) / TMA_TX, (g.Ny + TMA_TY - 1) / TMA_TY);
     { StageScope ts(h, "kernel:k_gu_tma");
-      k_mom_tma_p2<0><<<gr, b, TMA_NST * GU_STAGE * sizeof(float), h->stream>>>(g, t->gu, h->f.u, h->f.gn[0], h->carry[0]); }
+      k_mom_tma_p2<0><<<gr, b, MOM_NST * GU_STAGE * sizeof(float), h->stream>>>(g, t->gu, h->f.u, h->f.gn[0], h->carry[0]); }
     h->count_launch();
     { StageScope ts(h, "kernel:k_gv_tma");
-      k_mom_tma_p2<1><<<gr, b, TMA_NST * GV_STAGE * sizeof(float), h->stream>>>(g, t->gv, h->f.v, h->f.gn[1], h->carry[1]); }
+      k_mom_tma_p2<1><<<gr, b, MOM_NST * GV_STAGE * sizeof(float), h->stream>>>(g, t->gv, h->f.v, h->f.gn[1], h->carry[1]); }
     h->count_launch();
     return;
   }
@@ -874,6 +882,6 @@ void launch_tracer_tendency_tma(Handle* h) {
   const DevGrid& g = h->g;
   dim3 b(16, 10), gr((g.Nx + TR_TX - 1) / TR_TX, (g.Ny + TR_TY - 1) / TR_TY, 2);
   StageScope ts(h, "kernel:k_tracer_tma");
-  k_tracer_tma<<<gr, b, TMA_NST * TR_STAGE * sizeof(float), h->stream>>>(g, t->tr, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3], h->carry[2], h->carry[3]);
+  k_tracer_tma<<<gr, b, TR_NST * TR_STAGE * sizeof(float), h->stream>>>(g, t->tr, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3], h->carry[2], h->carry[3]);
   h->count_launch();
 }
