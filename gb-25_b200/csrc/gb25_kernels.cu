@@ -24,21 +24,46 @@ __global__ void k_halo_south_north(DevGrid g, HaloBatch hb, int three_d, int mod
   const int PX = g.PX, Hx = g.Hx, Hy = g.Hy, Ny = g.Ny, Nx = g.Nx;
   const int I = i + Hx - 1;
 #define A2(ii, jj) a[(ii) + PX * ((jj) + Hy - 1)]
+  // loads first, stores afterwards (the rows never overlap, but the compiler cannot know: a load-store chain would
+  // serialise Hy round trips per thread)
+  const bool h8 = Hy == 8 && Ny >= 8;
   if (mode_s == 1) {
-    if (hf.ly == 0) { for (int m = 1; m <= Hy; m++) A2(I, 1 - m) = A2(I, m); }
+    if (hf.ly == 0) {
+      if (h8) {
+        float t[8];
+#pragma unroll
+        for (int m = 1; m <= 8; m++) t[m - 1] = A2(I, m);
+#pragma unroll
+        for (int m = 1; m <= 8; m++) A2(I, 1 - m) = t[m - 1];
+      } else { for (int m = 1; m <= Hy; m++) A2(I, 1 - m) = A2(I, m); }
+    }
     else A2(I, 1) = 0.f;
   }
   if (mode_n == 1) {
-    if (hf.ly == 0) { for (int m = 1; m <= Hy; m++) A2(I, Ny + m) = A2(I, Ny + 1 - m); }
+    if (hf.ly == 0) {
+      if (h8) {
+        float t[8];
+#pragma unroll
+        for (int m = 1; m <= 8; m++) t[m - 1] = A2(I, Ny + 1 - m);
+#pragma unroll
+        for (int m = 1; m <= 8; m++) A2(I, Ny + m) = t[m - 1];
+      } else { for (int m = 1; m <= Hy; m++) A2(I, Ny + m) = A2(I, Ny + 1 - m); }
+    }
     else A2(I, Ny + 1) = 0.f;
   } else if (mode_n == 2) {
     int ip; float sg = hf.sign;
     if (hf.lx == 0) ip = Nx - i + 1;
     else { ip = Nx - i + 2; if (ip > Nx) { ip -= Nx; sg = fabsf(sg); } }
     const int IP = ip + Hx - 1;
-    for (int m = 1; m <= Hy; m++) {
-      const int js = hf.ly == 0 ? Ny - m : Ny - m + 1;
-      A2(I, Ny + m) = sg * A2(IP, js);
+    const int jo = hf.ly == 0 ? 0 : 1;
+    if (h8) {
+      float t[8];
+#pragma unroll
+      for (int m = 1; m <= 8; m++) t[m - 1] = A2(IP, Ny - m + jo);
+#pragma unroll
+      for (int m = 1; m <= 8; m++) A2(I, Ny + m) = sg * t[m - 1];
+    } else {
+      for (int m = 1; m <= Hy; m++) A2(I, Ny + m) = sg * A2(IP, Ny - m + jo);
     }
   }
 #undef A2
@@ -71,7 +96,17 @@ __global__ void k_halo_bottom_top(DevGrid g, HaloBatch hb) {
   const size_t n2 = g.n2; const int Hz = g.Hz, Nz = g.Nz;
 #define AK(kk) a[n2 * (size_t)((kk) + Hz - 1)]
   if (hf.lz == 0) {
-    for (int m = 1; m <= Hz; m++) { AK(1 - m) = AK(m); AK(Nz + m) = AK(Nz + 1 - m); }
+    // all loads first, then all stores (source and destination alias as far as the compiler knows: a
+    // load-store-load-store chain is 2 Hz dependent round trips to HBM per thread)
+    if (Hz == 8 && Nz >= 8) {
+      float lo[8], hi[8];
+#pragma unroll
+      for (int m = 1; m <= 8; m++) { lo[m - 1] = AK(m); hi[m - 1] = AK(Nz + 1 - m); }
+#pragma unroll
+      for (int m = 1; m <= 8; m++) { AK(1 - m) = lo[m - 1]; AK(Nz + m) = hi[m - 1]; }
+    } else {
+      for (int m = 1; m <= Hz; m++) { AK(1 - m) = AK(m); AK(Nz + m) = AK(Nz + 1 - m); }
+    }
   } else { AK(1) = 0.f; AK(Nz + 1) = 0.f; }
 #undef AK
 }
