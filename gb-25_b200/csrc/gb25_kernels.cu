@@ -3,6 +3,7 @@
 // /root/reference/src/precompile.jl:31-42.  All kernels are HBM/FP32-issue bound stencil or scan
 // work: x is the coalesced thread dimension everywhere, column scans run one thread per column.
 #include "gb25_internal.h"
+#include "gb25_packed.cuh"
 
 // =====================================================================================
 // Halo fills (row A2).  Bit-exact contract: copies and sign flips only.
@@ -245,8 +246,77 @@ void launch_compute_w(Handle* h) {
   dim3 b(128), gr((nx + 127) / 128, ny);
   k_compute_w<<<gr, b, 0, h->stream>>>(g, h->f.u, h->f.v, h->f.w); h->count_launch();
 }
+// Two x-adjacent columns per thread with the 55-term polynomial in packed FP32x2 (FFMA2): k_compute_p is bound by the
+// issue rate (ncu: issue slots 79 % active, 118 instructions per cell), and FFMA2 rounds each lane exactly like FFMA,
+// so the result is bit-identical.  Pairs start at i = -1 (8-byte aligned storage); columns outside 0..Nx+1 are not stored.
+__device__ __forceinline__ float2 pteos10_rho_prime(float2 Theta, float2 SA, float Z, float rho0, int with_r0) {
+  const float2 t = pmuls(Theta, 0.025f);
+  const float2 sa = pmuls(padd(SA, pbc(32.f)), 1.f / 40.18861714285714f);
+  const float2 s = make_float2(sqrtf(sa.x), sqrtf(sa.y));
+  const float z = Z * -1e-4f;
+#define PF(a, b, c) pfma(a, b, c)
+#define PC(x) pbc(x)
+  float2 r3 = PF(PC(3.7969820455e-01f), t, PF(PC(-1.8507636718e-02f), s, PC(-2.3342758797e-02f)));
+  float2 r2 = PF(t, PF(t, PC(-1.2419983026f), PF(s, PC(-2.1311365518e-01f), PC(2.0564311499f))),
+                 PF(s, PF(s, PC(2.5019633244f), PC(-4.9527603989f)), PC(2.0660924175f)));
+  float2 r1 = PF(t,
+                 PF(t,
+                    PF(t, PF(t, PC(5.5927935970e-01f), PF(s, PC(-5.5077101279e-01f), PC(-2.4649669534f))),
+                       PF(s, PF(s, PC(-1.8795372996f), PC(3.5063081279f)), PC(6.7080479603f))),
+                    PF(s, PF(s, PF(s, PC(-6.5399043664e-01f), PC(5.0042598061f)), PC(-4.4870114575f)), PC(-1.3336301113e+01f))),
+                 PF(s, PF(s, PF(s, PF(s, PC(6.6051753097f), PC(-3.0938076334e+01f)), PC(5.0774768218e+01f)), PC(-4.2549998214e+01f)), PC(1.9681925209e+01f)));
+  float2 q5 = PF(t, PC(-1.9083568888e-01f), PF(s, PC(4.8169980163e-01f), PC(5.4048723791e-01f)));
+  float2 q4 = PF(t, q5, PF(s, PF(s, PC(-5.3563304045f), PC(1.1311538584e+01f)), PC(-8.3627885467f)));
+  float2 q3 = PF(t, q4, PF(s, PF(s, PF(s, PC(-3.1742946532f), PC(1.9717078466e+01f)), PC(-3.3449108469e+01f)), PC(2.1661789529e+01f)));
+  float2 q2 = PF(t, q3, PF(s, PF(s, PF(s, PF(s, PC(-5.4723692739f), PC(2.9130021253e+01f)), PC(-6.0362551501e+01f)), PC(6.1548258127e+01f)), PC(-3.7074170417e+01f)));
+  float2 q1 = PF(t, q2, PF(s, PF(s, PF(s, PF(s, PF(s, PC(-1.9193502195f), PC(1.7681814114e+01f)), PC(-5.6888046321e+01f)), PC(8.1770425108e+01f)), PC(-6.5281885265e+01f)), PC(2.6010145068e+01f)));
+  float2 r0 = PF(t, q1,
+                 PF(s, PF(s, PF(s, PF(s, PF(s, PF(s, PC(-6.0579916612e+01f), PC(4.3227585684e+02f)), PC(-1.2849161071e+03f)), PC(2.0375295546e+03f)), PC(-1.7864682637e+03f)), PC(8.6672408165e+02f)), PC(8.0189615746e+02f)));
+  float2 r = PF(PF(PF(r3, PC(z), r2), PC(z), r1), PC(z), r0);
+#undef PF
+#undef PC
+  if (with_r0) {
+    const float rz = fmaf(fmaf(fmaf(fmaf(fmaf(fmaf(-1.7243708991e-03f, z, 1.5616995503e-02f), z, 6.4326772569e-02f), z, 2.2601900708e-01f), z, -5.2099962525f), z, 4.6494977072e+01f), z, 0.f);
+    r = padd(r, pbc(rz));
+  }
+  return psub(r, pbc(rho0));
+}
+__global__ void __launch_bounds__(128) k_compute_p2(DevGrid g, const float* __restrict__ T, const float* __restrict__ S, float* __restrict__ p) {
+  const int i = 2 * (blockIdx.x * blockDim.x + threadIdx.x) - 1;   // pair (i, i+1), i = -1, 1, ..., Nx+1
+  const int j = blockIdx.y;                                        // 0 .. Ny+1
+  if (i > g.Nx + 1) return;
+  const bool st0 = i >= 0, st1 = i + 1 <= g.Nx + 1;
+  const int q2 = id2(g, i, j);
+  size_t q3 = q2 + (size_t)g.n2 * (g.Nz + 1 + g.Hz - 1);
+  const float gr = g.g, r0 = g.rho0;
+  auto buoy = [&](size_t q, float z) {
+    const float2 rp = pteos10_rho_prime(*reinterpret_cast<const float2*>(T + q), *reinterpret_cast<const float2*>(S + q), z, r0, g.eos_r0);
+    return make_float2(-(gr * rp.x / r0), -(gr * rp.y / r0));
+  };
+  float2 bup = buoy(q3, g.zc[g.Nz + 1 + g.Hz - 1]);
+  float2 pk = make_float2(0.f, 0.f);
+#pragma unroll 2
+  for (int k = g.Nz; k >= 1; k--) {
+    q3 -= g.n2;
+    const float2 b = buoy(q3, g.zc[k + g.Hz - 1]);
+    const float2 bbar = pmuls(padd(b, bup), 0.5f);
+    const float dzf = g.dzf[k + 1 + g.Hz - 1];
+    pk.x = (k == g.Nz) ? -bbar.x * dzf : pk.x - bbar.x * dzf;
+    pk.y = (k == g.Nz) ? -bbar.y * dzf : pk.y - bbar.y * dzf;
+    if (st0 && st1) *reinterpret_cast<float2*>(p + q3) = pk;
+    else if (st0) p[q3] = pk.x;
+    else if (st1) p[q3 + 1] = pk.y;
+    bup = b;
+  }
+}
 void launch_compute_p(Handle* h) {
   const DevGrid& g = h->g;
+  if (h->use_packed && (g.Hx % 2) == 0 && (g.PX % 2) == 0) {
+    const int npairs = (g.Nx + 2) / 2 + 1;
+    dim3 b(128), gr((npairs + 127) / 128, g.Ny + 2);
+    k_compute_p2<<<gr, b, 0, h->stream>>>(g, h->f.T, h->f.S, h->f.p); h->count_launch();
+    return;
+  }
   dim3 b(128), gr((g.Nx + 2 + 127) / 128, g.Ny + 2);
   k_compute_p<<<gr, b, 0, h->stream>>>(g, h->f.T, h->f.S, h->f.p); h->count_launch();
 }

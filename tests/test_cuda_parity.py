@@ -231,6 +231,30 @@ def test_tma_kernels_equal_blocked_kernels(oracle_mod, monkeypatch, grid_type, N
     assert M.compare_states(rm_t, rm_b, include_halos=True, rtol=3e-6, atol=0.0, verbose=False, elementwise=1e-5)
 
 
+@pytest.mark.parametrize("grid_type,Nx,Ny,Nz", GRIDS + [("gaussian_islands", 130, 33, 7)])
+def test_packed_pressure_kernel_is_bit_identical(monkeypatch, grid_type, Nx, Ny, Nz):
+    """Row A4: k_compute_p2 evaluates TEOS-10 for two columns at once in FP32x2 (FFMA2 rounds each lane like FFMA):
+    the hydrostatic pressure anomaly, halo columns 0 and Nx+1 included, must equal the one-column-per-thread kernel
+    (GB25_PACKED=0) bit for bit, and nothing outside 0..Nx+1 may be touched."""
+    ms = []
+    for packed in ("1", "0"):
+        monkeypatch.setenv("GB25_PACKED", packed)
+        m = M.baroclinic_instability_model(M.B200(0), Nx, Ny, Nz, Δt=60.0, grid_type=grid_type)
+        M.set_baroclinic_instability(m)
+        rng = np.random.default_rng(5)
+        M.set(m, T=m.interior("T") + rng.random(m.interior("T").shape).astype(np.float32))
+        M.tupled_fill_halo_regions_workload(m)
+        M.compute_auxiliaries_workload(m)
+        m.synchronize()
+        ms.append(m)
+    monkeypatch.delenv("GB25_PACKED")
+    a, b = ms[0].parent("p"), ms[1].parent("p")
+    assert np.isfinite(a).all() and np.abs(a).max() > 0
+    assert np.array_equal(a, b), float(np.abs(a - b).max())
+    for m in ms:
+        m.close()
+
+
 @pytest.mark.parametrize("grid_type,Nx,Ny,Nz", GRIDS + [("gaussian_islands", 1440, 600, 4), ("simple_lat_lon", 96, 301, 4)])
 @pytest.mark.parametrize("bands", [None, "7"])
 def test_persistent_barotropic_kernel_equals_substep_kernels(monkeypatch, grid_type, Nx, Ny, Nz, bands):
