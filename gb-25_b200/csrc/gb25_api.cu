@@ -404,6 +404,19 @@ static void fill_prognostic(Handle* h) {
   HaloSpec s2[3] = {{f.eta, 0, 0, 1, 1.f}, {f.bu, 1, 0, 0, -1.f}, {f.bv, 0, 1, 0, -1.f}};
   launch_fill_halo(h, s2, 3, false);
 }
+// fused step path: ONE batch for the 3-D prognostic fields and the five 2-D fields whose halos the reference fills at
+// three different points of the step (GU,GV before the substeps, U,V after them, eta,U,V in update_state!).  Nothing reads
+// those halos in between (the substep kernels take GU,GV at interior points and start from the halos of the previous
+// step's fill), and the later fill overwrites every halo cell of the earlier ones, so the state after the step is the same —
+// with one exchange sequence between tiles instead of four.
+static void fill_prognostic_fused(Handle* h) {
+  StageScope t(h, "fill_halo_regions");
+  DevFields& f = h->f;
+  HaloSpec s[9] = {{f.u, 1, 0, 0, -1.f, 0}, {f.v, 0, 1, 0, -1.f, 0}, {f.T, 0, 0, 0, 1.f, 0}, {f.S, 0, 0, 0, 1.f, 0},
+                   {f.eta, 0, 0, 1, 1.f, 1}, {f.bu, 1, 0, 0, -1.f, 1}, {f.bv, 0, 1, 0, -1.f, 1},
+                   {f.gU, 1, 0, 0, -1.f, 1}, {f.gV, 0, 1, 0, -1.f, 1}};
+  launch_fill_halo(h, s, 9, true);
+}
 static void stage_mask(Handle* h) { StageScope t(h, "mask_immersed_fields"); launch_mask(h, false); }
 static void stage_aux(Handle* h) {
   if (h->use_fused && h->g.Nx % 2 == 0) { StageScope t(h, "compute_w_from_continuity"); launch_aux_columns(h); }
@@ -466,11 +479,15 @@ static void one_time_step_fused(Handle* h, float dt, float chi) {
   }
   {
     StageScope t(h, "split_explicit_free_surface");
-    HaloSpec sg[2] = {{f.gU, 1, 0, 0, -1.f}, {f.gV, 0, 1, 0, -1.f}};
-    launch_fill_halo(h, sg, 2, false);
+    if (overlap) {   // (the second-stream variant keeps the reference's fill points)
+      HaloSpec sg[2] = {{f.gU, 1, 0, 0, -1.f}, {f.gV, 0, 1, 0, -1.f}};
+      launch_fill_halo(h, sg, 2, false);
+    }
     launch_barotropic(h, dt);
-    HaloSpec sb[2] = {{f.bu, 1, 0, 0, -1.f}, {f.bv, 0, 1, 0, -1.f}};
-    launch_fill_halo(h, sb, 2, false);
+    if (overlap) {
+      HaloSpec sb[2] = {{f.bu, 1, 0, 0, -1.f}, {f.bv, 0, 1, 0, -1.f}};
+      launch_fill_halo(h, sb, 2, false);
+    }
   }
   h->time += (double)dt; h->iteration += 1; h->last_dt = dt;
   { StageScope t(h, "correct_velocities_and_cache"); launch_correct_fused(h); }
@@ -491,7 +508,7 @@ static void one_time_step_fused(Handle* h, float dt, float chi) {
     { StageScope t(h, "compute_w_from_continuity"); launch_aux_columns(h); }
     cudaStreamWaitEvent(h->stream, h->ev_join, 0);
   } else {
-    fill_prognostic(h);
+    fill_prognostic_fused(h);
     stage_aux(h);
   }
   stage_tend(h);

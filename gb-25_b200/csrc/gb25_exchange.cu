@@ -30,8 +30,8 @@ struct ExBlob {
 };
 
 // --------------------------------------------------------------------------------- device side
-struct PushField { const float* src; float* dst; int lx, ly, lz; float sign; };
-struct PushBatch { PushField f[4]; int n; };
+struct PushField { const float* src; float* dst; int lx, ly, lz; float sign; int flat; };
+struct PushBatch { PushField f[9]; int n; };
 
 // rows [srow, srow+nrows) of src -> rows [drow, ...) of dst; interior columns; planes [p0, p0+np)
 __global__ void k_push_rows(DevGrid g, PushBatch pb, int srow, int drow, int nrows, int p0, int np, int three_d) {
@@ -40,6 +40,7 @@ __global__ void k_push_rows(DevGrid g, PushBatch pb, int srow, int drow, int nro
   const int r = blockIdx.y % nrows, pl = blockIdx.y / nrows;
   if (pl >= np) return;
   const PushField pf = pb.f[blockIdx.z];
+  if (pf.flat) { if (pl > 0) return; three_d = 0; }
   const size_t po = three_d ? (size_t)g.n2 * (p0 + pl) : 0;
   pf.dst[po + (size_t)g.PX * (drow + r) + I] = pf.src[po + (size_t)g.PX * (srow + r) + I];
 }
@@ -49,6 +50,7 @@ __global__ void k_push_cols(DevGrid g, PushBatch pb, int scol, int dcol, int nco
   const int J = row0 + blockIdx.x * blockDim.y + threadIdx.y;
   if (cI >= ncols || J >= row0 + nrows_) return;
   const PushField pf = pb.f[blockIdx.z];
+  if (pf.flat) { if (blockIdx.y > 0) return; three_d = 0; }
   const size_t po = (three_d ? (size_t)g.n2 * blockIdx.y : 0) + (size_t)g.PX * J;
   pf.dst[po + dcol + cI] = pf.src[po + scol + cI];
 }
@@ -59,6 +61,7 @@ __global__ void k_push_fold(DevGrid g, PushBatch pb, int three_d, int nrows, int
   const int is = blockIdx.x * blockDim.x + threadIdx.x + 1;   // source column (local, 1-based)
   if (is > g.Nx) return;
   const PushField pf = pb.f[blockIdx.z];
+  if (pf.flat) three_d = 0;
   const int nk = three_d ? g.Nz + pf.lz : 1;
   const int k = blockIdx.y + 1;
   if (k > nk) return;
@@ -105,7 +108,7 @@ static PushBatch make_push(Handle* h, const HaloSpec* specs, int n, int slot, bo
     const int id = ex_field_id(h, specs[q].a);
     if (id < 0) continue;
     if (only_face_x && specs[q].lx == 0) continue;
-    pb.f[pb.n++] = PushField{specs[q].a, h->ex.to[slot].fld[id], specs[q].lx, specs[q].ly, specs[q].lz, specs[q].sign};
+    pb.f[pb.n++] = PushField{specs[q].a, h->ex.to[slot].fld[id], specs[q].lx, specs[q].ly, specs[q].lz, specs[q].sign, specs[q].flat};
   }
   return pb;
 }
@@ -190,7 +193,7 @@ void launch_fill_halo_dist(Handle* h, const HaloSpec* specs, int n, bool three_d
   }
   if (fold && c.Rx > 1) {
     int maxlz = 0;
-    for (int q = 0; q < n; q++) maxlz = max(maxlz, specs[q].lz);
+    for (int q = 0; q < n; q++) if (!specs[q].flat) maxlz = max(maxlz, specs[q].lz);
     const int nk = three_d ? g.Nz + maxlz : 1;
     PushBatch pb = make_push(h, specs, n, SLOT_FOLD);
     dim3 gr((g.Nx + 127) / 128, nk, pb.n);

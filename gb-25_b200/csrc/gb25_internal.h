@@ -8,7 +8,7 @@
 #include "../../include/gb25cuda.h"
 #include "gb25_device.cuh"
 
-struct HaloSpec { float* a; int lx, ly, lz; float sign; };
+struct HaloSpec { float* a; int lx, ly, lz; float sign; int flat; };   // flat = 1: a 2-D field riding in a batch of 3-D fields
 
 // ---- multi-GPU halo exchange over peer-mapped (CUDA IPC) memory, one process per GPU (gb25_exchange.cu)
 enum ExField { EX_U = 0, EX_V, EX_T, EX_S, EX_ETA, EX_BU, EX_BV, EX_GU, EX_GV, EX_NF };

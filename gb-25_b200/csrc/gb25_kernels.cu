@@ -8,8 +8,8 @@
 // =====================================================================================
 // Halo fills (row A2).  Bit-exact contract: copies and sign flips only.
 // =====================================================================================
-struct HaloField { float* a; int lx, ly, lz; float sign; };
-struct HaloBatch { HaloField f[4]; int n; };
+struct HaloField { float* a; int lx, ly, lz; float sign; int flat; };
+struct HaloBatch { HaloField f[9]; int n; };
 
 // south/north of 3-D or 2-D fields: threads over (i, k, field); loop over the halo depth
 // mode_s: 0 = nothing (a neighbour tile fills it), 1 = local wall BC.  mode_n: 0 = nothing, 1 = wall BC, 2 = local fold.
@@ -18,6 +18,7 @@ __global__ void k_halo_south_north(DevGrid g, HaloBatch hb, int three_d, int mod
   const int fidx = blockIdx.z;
   if (i > g.Nx) return;
   const HaloField hf = hb.f[fidx];
+  if (hf.flat) three_d = 0;
   const int nk = three_d ? g.Nz + hf.lz : 1;
   const int k = blockIdx.y + 1;
   if (k > nk) return;
@@ -76,6 +77,7 @@ __global__ void k_halo_fold_row(DevGrid g, HaloBatch hb, int three_d) {
   if (i > g.Nx) return;
   const HaloField hf = hb.f[blockIdx.z];
   if (hf.ly != 0) return;
+  if (hf.flat) three_d = 0;
   const int nk = three_d ? g.Nz + hf.lz : 1;
   const int k = blockIdx.y + 1;
   if (k > nk) return;
@@ -92,7 +94,7 @@ __global__ void k_halo_bottom_top(DevGrid g, HaloBatch hb) {
   const int j = blockIdx.y + 1;
   const HaloField hf = hb.f[blockIdx.z];
   const int jt = g.Ny + ((hf.ly && g.wall_n) ? 1 : 0);
-  if (i > g.Nx || j > jt) return;
+  if (i > g.Nx || j > jt || hf.flat) return;
   float* a = hf.a + id2(g, i, j);
   const size_t n2 = g.n2; const int Hz = g.Hz, Nz = g.Nz;
 #define AK(kk) a[n2 * (size_t)((kk) + Hz - 1)]
@@ -117,6 +119,7 @@ __global__ void k_halo_periodic_x(DevGrid g, HaloBatch hb, int three_d) {
   const int J = blockIdx.x * blockDim.y + threadIdx.y;  // storage row
   const int K = blockIdx.y;                       // storage plane
   if (t >= 2 * g.Hx || J >= g.PY) return;
+  if (hb.f[blockIdx.z].flat) { if (K > 0) return; three_d = 0; }
   float* a = hb.f[blockIdx.z].a + (three_d ? (size_t)g.n2 * K : 0) + (size_t)g.PX * J;
   // west halo cell I = t (t < Hx)  <- I + Nx ; east halo cell I = Nx + t (t >= Hx) <- I - Nx
   if (t < g.Hx) a[t] = a[t + g.Nx];
@@ -125,7 +128,10 @@ __global__ void k_halo_periodic_x(DevGrid g, HaloBatch hb, int three_d) {
 
 static HaloBatch make_batch(const HaloSpec* specs, int n, int* maxlz) {
   HaloBatch hb; hb.n = n; *maxlz = 0;
-  for (int q = 0; q < n; q++) { hb.f[q] = HaloField{specs[q].a, specs[q].lx, specs[q].ly, specs[q].lz, specs[q].sign}; *maxlz = max(*maxlz, specs[q].lz); }
+  for (int q = 0; q < n; q++) {
+    hb.f[q] = HaloField{specs[q].a, specs[q].lx, specs[q].ly, specs[q].lz, specs[q].sign, specs[q].flat};
+    if (!specs[q].flat) *maxlz = max(*maxlz, specs[q].lz);
+  }
   return hb;
 }
 void launch_halo_south_north(Handle* h, const HaloSpec* specs, int n, bool three_d, int mode_s, int mode_n) {
