@@ -36,6 +36,8 @@ WORKLOADS = {
     "latlon_128x64x8": ("simple_lat_lon", 128, 64, 8, 60.0),
     "tripolar_flat": ("tripolar", 1440, 600, 50, 60.0),              # profiling aid: no bathymetry => fast path only
     "latlon_1440x600x50": ("simple_lat_lon", 1440, 600, 50, 60.0),
+    # BASELINE.json configs[4]: the per-GPU tile of the 1/8-degree weak-scaling sweep (3.5e8 cells, ~30 GB of HBM)
+    "tripolar_eighth_degree_tile": ("gaussian_islands", 2880, 1200, 100, 30.0),
 }
 ALGORITHMIC_BYTES_PER_CELL_STEP = 104     # 26 Float32 words of compulsory 3-D traffic
 # algorithmic bytes per cell of one launch of each tendency kernel (DESIGN.md "kernels")
@@ -49,9 +51,9 @@ KERNEL_BYTES_PER_CELL = {"kernel:k_tracer_tendency_v2": (5 + 2) * 4,   # one lau
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` captures under
 # profiles/ (tripolar 1440x600x50 workload); None = not captured for this kernel version
 NCU_TRAFFIC_BYTES = {"kernel:k_tracer_tendency_v2": 1459761000 + 330897408,   # profiles/ncu_r1_v3_top_kernels.md
-                     # profiles/ncu_r1_v4_top_kernels.md (TMA + packed-FP32x2 kernels)
-                     "kernel:k_tracer_tma": 1514392000 + 332068096, "kernel:k_gu_tma": 1320836000 + 165283072,
-                     "kernel:k_gv_tma": 1384651000 + 168194560}
+                     # profiles/ncu_r1_v5_top_kernels.md (TMA + packed-FP32x2 kernels, 5/6-stage rings)
+                     "kernel:k_tracer_tma": 1516491000 + 328459520, "kernel:k_gu_tma": 1323222000 + 164882688,
+                     "kernel:k_gv_tma": 1403832000 + 165915136}
 
 
 def measured_peaks():
