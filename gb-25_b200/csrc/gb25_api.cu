@@ -197,8 +197,6 @@ extern "C" int gb25_destroy(gb25_handle* h) {
   if (!h) return GB25_ERR_INVALID;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
-  if (h->graph) cudaGraphDestroy(h->graph);
   exchange_close(h);
   tma_free(h);
   baro_plan_free(h);

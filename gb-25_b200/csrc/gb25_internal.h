@@ -44,8 +44,8 @@ struct gb25_handle {
   float* field_ptr[GB25_FIELD_COUNT];
   // scratch 3-D arrays shared by the v2 kernels: vorticity (F,F,C), delta_x(Ax u) and delta_y(Ay v) at (C,C,C)
   float *zeta = nullptr, *dxU = nullptr, *dyV = nullptr;
-  float *us2 = nullptr, *vs2 = nullptr;
-  float* carry[4] = {nullptr, nullptr, nullptr, nullptr};   // 2-D: vertical flux through the top face of the topmost generic cell (u, v, T, S)   // 2-D: column sums of the AB2-updated, masked velocities (fused path)
+  float *us2 = nullptr, *vs2 = nullptr;   // 2-D: column sums of the AB2-updated, masked velocities (fused path)
+  float* carry[4] = {nullptr, nullptr, nullptr, nullptr};   // 2-D: vertical flux through the top face of the topmost generic cell (u, v, T, S)
   // clock (model.clock)
   double time = 0.0;
   long iteration = 0;
@@ -63,11 +63,6 @@ struct gb25_handle {
   // staging for parent-shaped transfers
   float* stage_dev = nullptr;
   size_t stage_elems = 0;
-  // CUDA graph of one AB2 step (captured lazily for gb25_loop)
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t graph_exec = nullptr;
-  float graph_dt = 0.f;
-  long graph_launches = 0;
   bool use_fused = true;
   bool use_tma = true;
   bool use_overlap = false;            // run the T,S halo fill + hydrostatic pressure on a second stream during the substeps
@@ -135,7 +130,6 @@ void launch_ab2_fused(Handle* h, float dt, float chi);
 void launch_correct_fused(Handle* h);
 void launch_vdiff_explicit(Handle* h);
 void launch_implicit_columns(Handle* h, float dt, bool with_sums);
-void launch_barotropic_substeps(Handle* h, float dt);
 bool launch_barotropic_persistent(Handle* h, float dt);   // gb25_baro.cu; false: not applicable, use the substep kernels
 void baro_plan_free(Handle* h);
 int baro_check_timeout(Handle* h);
