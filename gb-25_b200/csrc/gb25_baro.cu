@@ -17,7 +17,8 @@
 //     because the partner's eta phase is not part of my own dependency chain);
 //   * the quads a neighbour waits for are computed first in every phase, the rest of the band hides the latency.
 // The arithmetic is, operation by operation, that of k_baro_eta / k_baro_uv / k_baro_finish (the FMUL / FFMA sequence
-// of their SASS is pinned with intrinsics; the parity test compares the two paths bit for bit).
+// of their SASS is pinned with intrinsics; the parity test compares the two paths bit for bit).  The three divisions per
+// point are the fast path of `/` without its range-check branch (div_nr, gb25_device.cuh): areas and spacings are normal numbers.
 #include <cstdlib>
 
 #include "gb25_internal.h"
@@ -173,7 +174,7 @@ __device__ __forceinline__ void eta_quad(const BandCtx& B, const DevGrid& g, con
   cst4<NCS, C_AZCC>(B, p, q2, az);
   lds4(e, B.s_eta + p);
 #pragma unroll
-  for (int c = 0; c < 4; c++) en[c] = __fsub_rn(e[c], __fdiv_rn(__fmul_rn(__fadd_rn(dU[c], dV[c]), B.dtau), az[c]));
+  for (int c = 0; c < 4; c++) en[c] = __fsub_rn(e[c], div_nr(__fmul_rn(__fadd_rn(dU[c], dV[c]), B.dtau), az[c]));
   *reinterpret_cast<float4*>(B.s_eta + p) = to_f4(en);
   if (jr == B.R - 1 && !B.top) ll_store4(a.ll_eta + (size_t)B.b * Nx + ir, en[0], en[1], en[2], en[3], seq);   // -> the band above
   if (XP && iq == B.NQ - 1) ll_store1(a.in_E + inbox_W(B.Ny) + (j - 1), en[3], seq);                           // -> east tile: eta(0, j)
@@ -193,7 +194,7 @@ __device__ __forceinline__ void uv_quad(const BandCtx& B, const DevGrid& g, cons
   else eW = ll_load1(a.inbox + inbox_W(B.Ny) + (j - 1), seq, B.G.s_abort, B.G.err);      // west tile: eta(0, j) of this substep
   cst4<NCS, C_DXFC>(B, p, q2, dxf);
 #pragma unroll
-  for (int c = 0; c < 4; c++) dxe[c] = __fdiv_rn(__fsub_rn(e[c], c > 0 ? e[c > 0 ? c - 1 : 0] : eW), dxf[c]);
+  for (int c = 0; c < 4; c++) dxe[c] = div_nr(__fsub_rn(e[c], c > 0 ? e[c > 0 ? c - 1 : 0] : eW), dxf[c]);
   if (j == 1 && (B.bflags & 2)) {
 #pragma unroll
     for (int c = 0; c < 4; c++) dye[c] = 0.f;
@@ -206,7 +207,7 @@ __device__ __forceinline__ void uv_quad(const BandCtx& B, const DevGrid& g, cons
     }
     cst4<NCS, C_DYCF>(B, p, q2, dyc);
 #pragma unroll
-    for (int c = 0; c < 4; c++) dye[c] = __fdiv_rn(__fsub_rn(e[c], eS[c]), dyc[c]);
+    for (int c = 0; c < 4; c++) dye[c] = div_nr(__fsub_rn(e[c], eS[c]), dyc[c]);
   }
   cst4<NCS, C_HFC>(B, p, q2, Hf); cst4<NCS, C_HCF>(B, p, q2, Hc);
   cst4<NCS, C_GU>(B, p, q2, GU); cst4<NCS, C_GV>(B, p, q2, GV);

@@ -258,7 +258,7 @@ void launch_compute_w(Handle* h) {
 __device__ __forceinline__ float2 pteos10_rho_prime(float2 Theta, float2 SA, float Z, float rho0, int with_r0) {
   const float2 t = pmuls(Theta, 0.025f);
   const float2 sa = pmuls(padd(SA, pbc(32.f)), 1.f / 40.18861714285714f);
-  const float2 s = make_float2(sqrtf(sa.x), sqrtf(sa.y));
+  const float2 s = make_float2(sqrt_nr(sa.x), sqrt_nr(sa.y));   // (S_A + 32) / 40.19 is of order one: no range check needed
   const float z = Z * -1e-4f;
 #define PF(a, b, c) pfma(a, b, c)
 #define PC(x) pbc(x)
@@ -295,9 +295,10 @@ __global__ void __launch_bounds__(128) k_compute_p2(DevGrid g, const float* __re
   const int q2 = id2(g, i, j);
   size_t q3 = q2 + (size_t)g.n2 * (g.Nz + 1 + g.Hz - 1);
   const float gr = g.g, r0 = g.rho0;
+  const float rr0 = rcp_refined(r0);   // rho0 ~ 1e3: the division by it needs no range check (div_by, gb25_device.cuh)
   auto buoy = [&](size_t q, float z) {
     const float2 rp = pteos10_rho_prime(*reinterpret_cast<const float2*>(T + q), *reinterpret_cast<const float2*>(S + q), z, r0, g.eos_r0);
-    return make_float2(-(gr * rp.x / r0), -(gr * rp.y / r0));
+    return make_float2(-div_by(gr * rp.x, r0, rr0), -div_by(gr * rp.y, r0, rr0));
   };
   float2 bup = buoy(q3, g.zc[g.Nz + 1 + g.Hz - 1]);
   float2 pk = make_float2(0.f, 0.f);

@@ -178,7 +178,10 @@ void launch_tracer_tendency_v2(Handle* h) {
 // dyV = delta_y(Ay v) at (C,C,C) and the vertical vorticity zeta at (F,F,C), with the immersed-aware
 // (conditional) differences already applied.  One thread per column of the extended range, marching k.
 // =====================================================================================
-__global__ void __launch_bounds__(128) k_aux_columns(DevGrid g, const float* __restrict__ u, const float* __restrict__ v,
+#ifndef AUX_MINB
+#define AUX_MINB 8
+#endif
+__global__ void __launch_bounds__(128, AUX_MINB) k_aux_columns(DevGrid g, const float* __restrict__ u, const float* __restrict__ v,
                                                      float* __restrict__ w, float* __restrict__ zeta, float* __restrict__ dxU,
                                                      float* __restrict__ dyV) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + (-g.Hx + 2);
@@ -199,8 +202,29 @@ __global__ void __launch_bounds__(128) k_aux_columns(DevGrid g, const float* __r
   size_t q3 = q2 + (size_t)n2 * g.Hz;  // k = 1
   float wk = 0.f;
   w[q3] = 0.f;
-  const float raz = 1.f;   // (divisions stay IEEE: w and zeta are compared element-wise)
-  (void)raz;
+  // (divisions stay IEEE: w and zeta are compared element-wise.)  With both areas inside the normal range the
+  // divisions are issued without the range-check branch (div_by, gb25_device.cuh) and with the reciprocals hoisted:
+  // the loads of four levels are then in flight together instead of one level's (0.33 -> 0.30 ms at 64 registers; 96 registers 0.35 ms, 40 registers 0.48 ms)
+  const bool safe = az > 1e-10f && az < 1e30f && azff > 1e-10f && azff < 1e30f;
+  if (safe) {
+    const float raz = rcp_refined(az), razff = rcp_refined(azff);
+#pragma unroll 4
+    for (int k = 1; k <= g.Nz; k++, q3 += n2) {
+      const float dz = g.dzc[k + g.Hz - 1];
+      const float u0 = u[q3], v0 = v[q3];
+      const float dU = dyE * dz * u[q3 + 1] - dyW * dz * u0;
+      const float dV = dxN * dz * v[q3 + PX] - dxS * dz * v0;
+      dxU[q3] = dU; dyV[q3] = dV;
+      wk = wk - div_by(dU + dV, az, raz);
+      w[q3 + n2] = wk;
+      float d1 = zyE * v0 - zyW * v[q3 - 1];
+      float d2 = zxN * u0 - zxS * u[q3 - PX];
+      if (k <= t1) d1 = 0.f;
+      if (k <= t2) d2 = 0.f;
+      zeta[q3] = div_by(d1 - d2, azff, razff);
+    }
+    return;
+  }
 #pragma unroll 4
   for (int k = 1; k <= g.Nz; k++, q3 += n2) {
     const float dz = g.dzc[k + g.Hz - 1];
