@@ -22,6 +22,8 @@ __device__ __forceinline__ float2 pmuls(float2 a, float s) { return pmul(a, pbc(
 __device__ __forceinline__ float2 pfmas(float2 a, float s, float2 c) { return pfma(a, pbc(s), c); }   // a*s + c
 __device__ __forceinline__ float2 prcp(float2 a) { return make_float2(frcp(a.x), frcp(a.y)); }
 __device__ __forceinline__ float2 prcp_exact(float2 a) { return make_float2(1.f / a.x, 1.f / a.y); }   // IEEE: feeds a model field
+// the same correctly rounded reciprocal without the range-check branch of `1.f / x` (cell volumes are normal numbers)
+__device__ __forceinline__ float2 prcp_nr(float2 a) { return make_float2(rcp_refined(a.x), rcp_refined(a.y)); }
 
 // smoothness indicators / 3.25 (see beta5_* in gb25_device.cuh)
 __device__ __forceinline__ float2 pbeta0(float2 a, float2 b, float2 c) {

@@ -591,7 +591,7 @@ k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const float* __rest
           dpp = psub(ldpa(P), ldpa(P - GV_PD));
         }
         const float2 Wt = pmul(wt, pvert(WA, WB, zbuf(g, kbA, k + 1, 3), zbuf(g, kbB, k + 1, 3), wt, eps));
-        const float2 Vterm = pmul(pmuls(rAz, 1.f / dz), padd(Phi, psub(Wt, Wb)));
+        const float2 Vterm = pmul(pmuls(rAz, rcp_refined(dz)), padd(Phi, psub(Wt, Wb)));   // (1/dz without the range-check branch)
         Wb = Wt;
         const float2 ct = pmul(pmul(fbar, oavg), rm1);          // Gu: -(-ct) ; Gv: -(+ct)
         const float2 sum = padd(padd(Hterm, Vterm), pmul(Bsum, rm1));
@@ -763,7 +763,7 @@ k_tracer_tma(DevGrid g, const __grid_constant__ TmaMaps5 tm, const float* __rest
         }
         const float2 azp = make_float2(az[r][0], az[r][1]);
         const float2 ft = pmul(pmul(azp, ww), rec);
-        const float2 rV = prcp_exact(pmuls(azp, dz));
+        const float2 rV = prcp_nr(pmuls(azp, dz));
         const float fxr0 = r == 0 ? fx[0].x : fx[0].y, fxr1 = r == 0 ? fx[1].x : fx[1].y, fxr2 = r == 0 ? fx[2].x : fx[2].y;
         const float2 dfx = make_float2(fxr1 - fxr0, fxr2 - fxr1);
         const float2 dfy = psub(fy[r + 1], fy[r]);
