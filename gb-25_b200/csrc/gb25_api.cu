@@ -305,7 +305,7 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     h->allocs.push_back(*sp);
     CKC(ckcuda(cudaMemsetAsync(*sp, 0, n3 * sizeof(float), h->stream), "cudaMemset"));
   }
-  for (float** sp : {&h->us2, &h->vs2, &h->carry[0], &h->carry[1], &h->carry[2], &h->carry[3]}) {
+  for (float** sp : {&h->us2, &h->vs2, &h->corr_u, &h->corr_v, &h->carry[0], &h->carry[1], &h->carry[2], &h->carry[3]}) {
     cudaError_t ce = cudaMalloc(sp, n2 * sizeof(float));
     if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc scratch: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
     h->allocs.push_back(*sp);

@@ -45,6 +45,7 @@ struct gb25_handle {
   // scratch 3-D arrays shared by the v2 kernels: vorticity (F,F,C), delta_x(Ax u) and delta_y(Ay v) at (C,C,C)
   float *zeta = nullptr, *dxU = nullptr, *dyV = nullptr;
   float *us2 = nullptr, *vs2 = nullptr;   // 2-D: column sums of the AB2-updated, masked velocities (fused path)
+  float *corr_u = nullptr, *corr_v = nullptr;   // 2-D: unmasked barotropic transports for the streamed corrector
   float* carry[4] = {nullptr, nullptr, nullptr, nullptr};   // 2-D: vertical flux through the top face of the topmost generic cell (u, v, T, S)
   // clock (model.clock)
   double time = 0.0;

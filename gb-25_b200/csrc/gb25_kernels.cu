@@ -2,6 +2,8 @@
 // One kernel per stage of the Oceananigans HydrostaticFreeSurfaceModel step, in the order of
 // /root/reference/src/precompile.jl:31-42.  All kernels are HBM/FP32-issue bound stencil or scan
 // work: x is the coalesced thread dimension everywhere, column scans run one thread per column.
+#include <cstdlib>
+
 #include "gb25_internal.h"
 #include "gb25_packed.cuh"
 
@@ -621,8 +623,78 @@ void launch_ab2_fused(Handle* h, float dt, float chi) {
   StageScope ts(h, "kernel:k_ab2_fused");
   k_ab2_fused<<<gr, b, 0, h->stream>>>(g, h->f, h->us2, h->vs2, dt, chi); h->count_launch();
 }
+// The corrector has no dependence along k (the correction is a 2-D field), so the 3-D part streams: one thread per four
+// x-adjacent cells and CORR_KCH levels, 128-bit accesses in memory order, instead of one thread marching a whole column.
+// Same per-cell expressions as k_correct_fused.  The 2-D part (filtered-state scratch, U,V masks, G- <- Gn of the
+// barotropic tendencies) runs first in its own small kernel and leaves the unmasked transports in two scratch arrays,
+// from which the 3-D kernel recomputes the correction.
+#define CORR_KCH 10
+__global__ void __launch_bounds__(128) k_correct_3d(DevGrid g, DevFields f, const float* __restrict__ us2, const float* __restrict__ vs2,
+                                                    const float* __restrict__ ubar, const float* __restrict__ vbar) {
+  const int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x) + 1, j = blockIdx.y + 1;
+  if (i > g.Nx) return;
+  const int k0 = blockIdx.z * CORR_KCH + 1, k1 = min(k0 + CORR_KCH - 1, g.Nz);
+  const int q2 = id2(g, i, j), n2 = g.n2;
+  const float4 su = *reinterpret_cast<const float4*>(us2 + q2), sv = *reinterpret_cast<const float4*>(vs2 + q2);
+  const float4 bu = *reinterpret_cast<const float4*>(ubar + q2), bv = *reinterpret_cast<const float4*>(vbar + q2);
+  const float4 hf = *reinterpret_cast<const float4*>(g.Hfc + q2), hc = *reinterpret_cast<const float4*>(g.Hcf + q2);
+  const float cu[4] = {(bu.x - su.x) / hf.x, (bu.y - su.y) / hf.y, (bu.z - su.z) / hf.z, (bu.w - su.w) / hf.w};
+  const float cv[4] = {(bv.x - sv.x) / hc.x, (bv.y - sv.y) / hc.y, (bv.z - sv.z) / hc.z, (bv.w - sv.w) / hc.w};
+  int kbu[4], kbv[4];   // highest solid level next to the u / v node
+  {
+    const int kw = g.kb[q2 - 1];
+    const int kc[4] = {g.kb[q2], g.kb[q2 + 1], g.kb[q2 + 2], g.kb[q2 + 3]};
+    const bool ywall = y_outside(g, j) || y_outside(g, j - 1);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      kbu[c] = max(kc[c], c == 0 ? kw : kc[c > 0 ? c - 1 : 0]);
+      kbv[c] = ywall ? GB25_BIG : max(kc[c], (int)g.kb[q2 - g.PX + c]);
+    }
+  }
+  const bool imm = g.immersed;
+  size_t q3 = q2 + (size_t)n2 * (k0 + g.Hz - 1);
+#pragma unroll 2
+  for (int k = k0; k <= k1; k++, q3 += n2) {
+    float4 u4 = *reinterpret_cast<const float4*>(f.u + q3), v4 = *reinterpret_cast<const float4*>(f.v + q3);
+    float un[4] = {u4.x + cu[0], u4.y + cu[1], u4.z + cu[2], u4.w + cu[3]};
+    float vn[4] = {v4.x + cv[0], v4.y + cv[1], v4.z + cv[2], v4.w + cv[3]};
+    if (imm) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        if (k <= kbu[c]) un[c] = 0.f;
+        if (k <= kbv[c]) vn[c] = 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(f.u + q3) = make_float4(un[0], un[1], un[2], un[3]);
+    *reinterpret_cast<float4*>(f.v + q3) = make_float4(vn[0], vn[1], vn[2], vn[3]);
+  }
+}
+// 2-D part of the corrector; leaves the unmasked transports in ubar / vbar for k_correct_3d
+__global__ void k_correct_2d(DevGrid g, DevFields f, const float* __restrict__ us2, const float* __restrict__ vs2,
+                             float* __restrict__ ubar, float* __restrict__ vbar) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.Nx) return;
+  const int q2 = id2(g, i, j);
+  f.fu[q2] = us2[q2]; f.fv[q2] = vs2[q2];     // filtered_state.U/V are reused as scratch by the reference
+  ubar[q2] = f.bu[q2]; vbar[q2] = f.bv[q2];
+  if (g.immersed) {   // barotropic transports: masked where the surface node is peripheral (decision U11)
+    const int kb0 = g.kb[q2], kbw = g.kb[q2 - 1], kbs = g.kb[q2 - g.PX];
+    const bool ywall = y_outside(g, j) || y_outside(g, j - 1);
+    if (g.Nz <= kb0 || g.Nz <= kbw) f.bu[q2] = 0.f;
+    if (ywall || g.Nz <= kb0 || g.Nz <= kbs) f.bv[q2] = 0.f;
+  }
+  f.gmU[q2] = f.gU[q2]; f.gmV[q2] = f.gV[q2];
+}
 void launch_correct_fused(Handle* h) {
   const DevGrid& g = h->g;
+  static const bool streamed = []() { const char* e = getenv("GB25_CORRECT_3D"); return !(e && e[0] == '0'); }();
+  if (streamed && g.Nx % 4 == 0 && g.Hx % 4 == 0 && g.PX % 4 == 0) {
+    dim3 b2(128), g2((g.Nx + 127) / 128, g.Ny);
+    k_correct_2d<<<g2, b2, 0, h->stream>>>(g, h->f, h->us2, h->vs2, h->corr_u, h->corr_v); h->count_launch();
+    dim3 b(128), gr((g.Nx / 4 + 127) / 128, g.Ny, (g.Nz + CORR_KCH - 1) / CORR_KCH);
+    k_correct_3d<<<gr, b, 0, h->stream>>>(g, h->f, h->us2, h->vs2, h->corr_u, h->corr_v); h->count_launch();
+    return;
+  }
   dim3 b(128), gr((g.Nx + 127) / 128, g.Ny);
   k_correct_fused<<<gr, b, 0, h->stream>>>(g, h->f, h->us2, h->vs2); h->count_launch();
 }
