@@ -617,10 +617,80 @@ __global__ void k_correct_fused(DevGrid g, DevFields f, const float* __restrict_
   }
   f.gmU[q2] = f.gU[q2]; f.gmV[q2] = f.gV[q2];
 }
+// The same stage in two kernels: the u, v half needs the column sums (thread per column, as above); the T, S half has no
+// dependence along k and streams like k_correct_3d (one thread per four x-adjacent cells x AB2_KCH levels, 128-bit accesses).
+#define AB2_KCH 10
+__global__ void __launch_bounds__(128) k_ab2_uv(DevGrid g, DevFields f, float* __restrict__ us2, float* __restrict__ vs2, float dt, float chi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.Nx) return;
+  const int q2 = id2(g, i, j), n2 = g.n2;
+  const float c1 = 1.5f + chi, c2 = 0.5f + chi;
+  const float ne = (chi != -0.5f) ? 1.f : 0.f;
+  const int kb0 = g.kb[q2], kbw = g.kb[q2 - 1], kbs = g.kb[q2 - g.PX];
+  const bool ywall = y_outside(g, j) || y_outside(g, j - 1);
+  const bool imm = g.immersed;
+  float su = 0.f, sv = 0.f, bu = 0.f, bv = 0.f;
+  size_t q3 = q2 + (size_t)n2 * g.Hz;
+  for (int k = 1; k <= g.Nz; k++, q3 += n2) {
+    const float dz = g.dzc[k + g.Hz - 1];
+    const float gu = c1 * f.gn[0][q3] - c2 * f.gm[0][q3] * ne;
+    const float gv = c1 * f.gn[1][q3] - c2 * f.gm[1][q3] * ne;
+    const bool pu = k <= kb0 || k <= kbw;
+    const bool pv = ywall || k <= kb0 || k <= kbs;
+    const float tu = dz * (pu ? 0.f : gu), tv = dz * (pv ? 0.f : gv);
+    su = (k == 1) ? tu : su + tu;
+    sv = (k == 1) ? tv : sv + tv;
+    float un = f.u[q3] + dt * gu, vn = f.v[q3] + dt * gv;
+    if (imm) {
+      if (pu) un = 0.f;
+      if (pv) vn = 0.f;
+    }
+    f.u[q3] = un; f.v[q3] = vn;
+    const float wu = dz * un, wv = dz * vn;
+    bu = (k == 1) ? wu : bu + wu;
+    bv = (k == 1) ? wv : bv + wv;
+  }
+  f.gU[q2] = su; f.gV[q2] = sv;
+  us2[q2] = bu; vs2[q2] = bv;
+}
+__global__ void __launch_bounds__(128) k_ab2_ts_3d(DevGrid g, DevFields f, float dt, float chi) {
+  const int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x) + 1, j = blockIdx.y + 1;
+  if (i > g.Nx) return;
+  const int k0 = blockIdx.z * AB2_KCH + 1, k1 = min(k0 + AB2_KCH - 1, g.Nz);
+  const int q2 = id2(g, i, j), n2 = g.n2;
+  const float c1 = 1.5f + chi, c2 = 0.5f + chi;
+  const int kb[4] = {g.kb[q2], g.kb[q2 + 1], g.kb[q2 + 2], g.kb[q2 + 3]};
+  const bool imm = g.immersed;
+  size_t q3 = q2 + (size_t)n2 * (k0 + g.Hz - 1);
+#pragma unroll 2
+  for (int k = k0; k <= k1; k++, q3 += n2) {
+#pragma unroll
+    for (int q = 2; q < 4; q++) {
+      float* __restrict__ x = q == 2 ? f.T : f.S;
+      const float4 x4 = *reinterpret_cast<const float4*>(x + q3);
+      const float4 n4 = *reinterpret_cast<const float4*>(f.gn[q] + q3), m4 = *reinterpret_cast<const float4*>(f.gm[q] + q3);
+      float xn[4] = {x4.x + dt * (c1 * n4.x - c2 * m4.x), x4.y + dt * (c1 * n4.y - c2 * m4.y),
+                     x4.z + dt * (c1 * n4.z - c2 * m4.z), x4.w + dt * (c1 * n4.w - c2 * m4.w)};
+      if (imm) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) if (k <= kb[c]) xn[c] = 0.f;
+      }
+      *reinterpret_cast<float4*>(x + q3) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+    }
+  }
+}
 void launch_ab2_fused(Handle* h, float dt, float chi) {
   const DevGrid& g = h->g;
-  dim3 b(128), gr((g.Nx + 127) / 128, g.Ny);
   StageScope ts(h, "kernel:k_ab2_fused");
+  static const bool split = []() { const char* e = getenv("GB25_AB2_SPLIT_TS"); return !(e && e[0] == '0'); }();
+  if (split && g.Nx % 4 == 0 && g.Hx % 4 == 0 && g.PX % 4 == 0) {
+    dim3 b(128), gr((g.Nx + 127) / 128, g.Ny);
+    k_ab2_uv<<<gr, b, 0, h->stream>>>(g, h->f, h->us2, h->vs2, dt, chi); h->count_launch();
+    dim3 g3((g.Nx / 4 + 127) / 128, g.Ny, (g.Nz + AB2_KCH - 1) / AB2_KCH);
+    k_ab2_ts_3d<<<g3, b, 0, h->stream>>>(g, h->f, dt, chi); h->count_launch();
+    return;
+  }
+  dim3 b(128), gr((g.Nx + 127) / 128, g.Ny);
   k_ab2_fused<<<gr, b, 0, h->stream>>>(g, h->f, h->us2, h->vs2, dt, chi); h->count_launch();
 }
 // The corrector has no dependence along k (the correction is a 2-D field), so the 3-D part streams: one thread per four
