@@ -142,7 +142,7 @@ def run_reference_arm(args, workload):
     grid_type, Nx, Ny, Nz, dt = WORKLOADS[workload]
     sx, sy = (4, 4) if Nx >= 512 else (1, 1)
     nx, ny = Nx // sx, Ny // sy
-    cores = os.cpu_count() or 1
+    cores = O.set_num_threads()      # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     m = M.baroclinic_instability_model(O.CPUOracle(np.float32), nx, ny, Nz, Δt=dt * sx, grid_type=grid_type,
                                        model_cls=O.OracleModel)
     synthetic_state(m)
@@ -169,6 +169,7 @@ def cpu_baseline_sample(workload, budget_s=20.0):
     from gb25_b200 import model as M
     from oracle import oracle as O
     O.build()
+    cores = O.set_num_threads()
     grid_type, Nx, Ny, Nz, dt = WORKLOADS[workload]
     sx = 4 if Nx >= 512 else 1
     nx, ny = Nx // sx, Ny // sx
@@ -184,7 +185,7 @@ def cpu_baseline_sample(workload, budget_s=20.0):
         el = time.perf_counter() - t0
         if el > budget_s or n >= 50:
             break
-    return {"value": nx * ny * Nz * n / el, "unit": "cell-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
+    return {"value": nx * ny * Nz * n / el, "unit": "cell-steps/s", "cores": cores, "kind": "port",
             "sample": f"CPU oracle (C++/OpenMP restatement, not Oceananigans: no Julia in the image) on {grid_type} "
                       f"{nx}x{ny}x{Nz}, {n} steps in {el:.1f} s"}
 

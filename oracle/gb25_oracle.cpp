@@ -33,6 +33,9 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 extern "C" {
 struct OConfig {
@@ -849,3 +852,19 @@ struct Oracle {
 
 ORACLE_API(f32, float)
 ORACLE_API(f64, double)
+
+// ---- OpenMP thread control for the timed CPU baseline (torchrun exports OMP_NUM_THREADS=1 to its workers)
+extern "C" void gb25o_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+extern "C" int gb25o_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

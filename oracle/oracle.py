@@ -43,12 +43,21 @@ def build(force=False):
     return LIB_PATH
 
 
+def set_num_threads(n=None):
+    """OpenMP threads of the oracle (default: every host core).  Returns the count in effect."""
+    lib = load()
+    lib.gb25o_set_num_threads(int(n or os.cpu_count() or 1))
+    return int(lib.gb25o_max_threads())
+
+
 def load():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             build()
         _lib = C.CDLL(LIB_PATH)
+        _lib.gb25o_set_num_threads.argtypes = [C.c_int]
+        _lib.gb25o_max_threads.restype = C.c_int
         for suf, ft in (("f32", C.c_float), ("f64", C.c_double)):
             P = C.POINTER(ft)
             getattr(_lib, f"gb25o_create_{suf}").restype = C.c_void_p
