@@ -48,12 +48,27 @@ KERNEL_BYTES_PER_CELL = {"kernel:k_tracer_tendency_v2": (5 + 2) * 4,   # one lau
                          "kernel:k_gv_tma": (4 + 1) * 4,
                          "kernel:k_ab2_fused": 16 * 4,                  # read 4 fields + 8 G, write 4 fields
                          "momentum_tendencies": 2 * (4 + 1) * 4, "tracer_tendencies": (5 + 2) * 4}
-# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full` captures under
-# profiles/ (tripolar 1440x600x50 workload); None = not captured for this kernel version
-NCU_TRAFFIC_BYTES = {"kernel:k_tracer_tendency_v2": 1459761000 + 330897408,   # profiles/ncu_r1_v3_top_kernels.md
-                     # profiles/ncu_r1_v5_top_kernels.md (TMA + packed-FP32x2 kernels, 5/6-stage rings)
-                     "kernel:k_tracer_tma": 1516491000 + 328459520, "kernel:k_gu_tma": 1323222000 + 164882688,
-                     "kernel:k_gv_tma": 1403832000 + 165915136}
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) comes from profiles/ncu_traffic.json, written by
+# scripts/ncu_table.py from an `ncu --set full` capture; it is reported only when the capture was taken with the kernel
+# sources that are being timed (sha256 over gb-25_b200/csrc), otherwise `traffic` is null.
+def kernel_source_sha():
+    import hashlib
+    d = os.path.join(ROOT, "gb-25_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return {}, "no capture"
+    d = json.load(open(p))
+    if d.get("kernel_source_sha") != kernel_source_sha():
+        return {}, f"stale capture ({d.get('kernel_source_sha')}): kernel sources changed since"
+    return d.get("kernels", {}), d.get("capture", "profiles/ncu_traffic.json")
 
 
 def measured_peaks():
@@ -129,22 +144,46 @@ def synthetic_state(model, seed=42):
     M.set(model, u=(1e-3 * rng.random(shp, dtype=np.float32)), v=(1e-3 * rng.random(model.interior("v").shape, dtype=np.float32)))
 
 
+def _oracle_model(grid_type, nx, ny, Nz, dt):
+    from gb25_b200 import model as M
+    from oracle import oracle as O
+    from gb25_b200.config import PhysicsConfig
+    # sum-of-squares smoothness indicators: the expanded form of the recalled reference NaNs in Float32 at these sizes
+    # (DESIGN.md deviation D1); same flop count to within a few per cent
+    return M.baroclinic_instability_model(O.CPUOracle(np.float32), nx, ny, Nz, Δt=dt, grid_type=grid_type,
+                                          model_cls=O.OracleModel, physics=PhysicsConfig(oracle_beta_form=1))
+
+
+def _scaled_dims(workload, shrink):
+    grid_type, Nx, Ny, Nz, dt = WORKLOADS[workload]
+    return grid_type, Nx // shrink, Ny // shrink, Nz, dt * shrink
+
+
 def run_reference_arm(args, workload):
-    """--impl reference: the reference's CPU implementation of the path.  Oceananigans CPU() cannot run here
-    (no Julia in the image), so this is the CPU oracle port with all host threads, on a bounded
-    sample of the same workload (a reduced-size tile of the same grid family and vertical resolution)."""
+    """--impl reference: the reference's CPU implementation of the path.  Oceananigans CPU() cannot run here (no
+    Julia in the image), so this is the CPU oracle port (`kind: "port"`) with all host threads.  At N = 1
+    it runs the SAME configuration as our arm (full size) when K + W steps fit a few minutes; otherwise, and for
+    N > 1 (rank 0 alone works), a bounded sample: a reduced tile of the same grid family whose true size and dt are
+    what `config` reports, with `same_config: false`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from gb25_b200 import model as M
     from oracle import oracle as O
     O.build()
-    grid_type, Nx, Ny, Nz, dt = WORKLOADS[workload]
-    sx, sy = (4, 4) if Nx >= 512 else (1, 1)
-    nx, ny = Nx // sx, Ny // sy
     cores = O.set_num_threads()      # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
-    m = M.baroclinic_instability_model(O.CPUOracle(np.float32), nx, ny, Nz, Δt=dt * sx, grid_type=grid_type,
-                                       model_cls=O.OracleModel)
+    grid_type, Nx, Ny, Nz, dt = WORKLOADS[workload]
+    budget_s = float(os.environ.get("GB25_REFERENCE_BUDGET_S", "240"))
+    nsteps_total = args.steps + max(args.warmup, 1) + 1          # first_time_step costs about two steps
+    shrink = 1
+    # measured on the round-1 box (16 cores): 6.5e6 cell-steps/s; pick the largest tile of the family that fits the budget
+    est_rate = 4.0e5 * cores
+    while Nx // shrink >= 64 and (Nx // shrink) * (Ny // shrink) * Nz * nsteps_total / est_rate > budget_s and shrink < 8:
+        shrink *= 2
+    if Nx * Ny * Nz < 1e6:
+        shrink = 1
+    grid_type, nx, ny, Nz, dts = _scaled_dims(workload, shrink)
+    m = _oracle_model(grid_type, nx, ny, Nz, dts)
     synthetic_state(m)
     M.first_time_step(m)
     for _ in range(max(args.warmup - 1, 0)):
@@ -153,28 +192,38 @@ def run_reference_arm(args, workload):
     for _ in range(args.steps):
         M.time_step(m)
     el = time.perf_counter() - t0
+    finite = bool(np.isfinite(m.interior("eta")).all())
     cells = nx * ny * Nz
     val = cells * args.steps / el
-    sample = f"{grid_type} {nx}x{ny}x{Nz} ({args.steps} steps; 1/{sx * sy} of the {Nx}x{Ny}x{Nz} workload), OpenMP"
+    same = shrink == 1 and args.gpus == 1
+    sample = (f"{grid_type} {nx}x{ny}x{Nz}, dt = {dts:g} s, {args.steps} timed steps" +
+              ("" if shrink == 1 else f" (1/{shrink * shrink} of the {Nx}x{Ny}x{Nz} per-GPU tile)") +
+              f"; CPU oracle port (C++/OpenMP, {cores} threads), not Oceananigans CPU(): no Julia in the image")
     line = {"impl": "reference", "metric": "cell_steps_per_s", "value": val, "unit": "cell-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "grid": grid_type, "Nx": Nx, "Ny": Ny, "Nz": Nz, "dt": dt},
+            "config": {"workload": workload, "grid": grid_type, "Nx": nx, "Ny": ny, "Nz": Nz, "dt": dts,
+                       "same_config": same, "kind": "port", "state_finite": finite},
             "cpu_baseline": {"value": val, "unit": "cell-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+    if not finite:
+        raise SystemExit("reference arm: state is not finite")
 
 
 def cpu_baseline_sample(workload, budget_s=20.0):
+    """The CPU oracle on the box's host cores, on the bench's own configuration (full size), for a bounded number of
+    steps (about `budget_s` of stepping after the first step)."""
     from gb25_b200 import model as M
     from oracle import oracle as O
     O.build()
     cores = O.set_num_threads()
     grid_type, Nx, Ny, Nz, dt = WORKLOADS[workload]
-    sx = 4 if Nx >= 512 else 1
-    nx, ny = Nx // sx, Ny // sx
-    m = M.baroclinic_instability_model(O.CPUOracle(np.float32), nx, ny, Nz, Δt=dt * sx, grid_type=grid_type,
-                                       model_cls=O.OracleModel)
+    shrink = 1
+    while Nx // shrink * (Ny // shrink) * Nz > 6e7:      # the 1/8-degree tile: sample a quarter-size tile
+        shrink *= 2
+    grid_type, nx, ny, Nz, dts = _scaled_dims(workload, shrink)
+    m = _oracle_model(grid_type, nx, ny, Nz, dts)
     synthetic_state(m)
     M.first_time_step(m)
     t0 = time.perf_counter()
@@ -187,7 +236,7 @@ def cpu_baseline_sample(workload, budget_s=20.0):
             break
     return {"value": nx * ny * Nz * n / el, "unit": "cell-steps/s", "cores": cores, "kind": "port",
             "sample": f"CPU oracle (C++/OpenMP restatement, not Oceananigans: no Julia in the image) on {grid_type} "
-                      f"{nx}x{ny}x{Nz}, {n} steps in {el:.1f} s"}
+                      f"{nx}x{ny}x{Nz}, dt = {dts:g} s, {n} steps in {el:.1f} s"}
 
 
 def main():
@@ -199,6 +248,10 @@ def main():
     ap.add_argument("--workload", default="tripolar_quarter_degree", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = the workload's tile on every GPU (default); strong = the workload's GLOBAL grid "
+                         "split over (Rx, Ry) = factors(N) (BASELINE.json configs[2])")
+    ap.add_argument("--no-partition-check", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args, args.workload)
@@ -225,6 +278,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     grid_type, Nx, Ny, Nz, dt = WORKLOADS[args.workload]
     Rx, Ry = sharding.factors(world)
+    if args.scaling == "strong" and world > 1:
+        if Nx % Rx or Ny % Ry:
+            raise SystemExit(f"--scaling strong: {Nx}x{Ny} is not divisible by the partition {Rx}x{Ry}")
+        Nx, Ny = Nx // Rx, Ny // Ry
+
+    # N > 1: before anything is timed, the partitioned run must equal the single-GPU run of the same global problem
+    # bit for bit (the reference's sharded correctness protocol on 64x48x10 tiles, both grids)
+    bit_identical = None
+    if world > 1 and not args.no_partition_check:
+        from gb25_b200 import distributed as D
+        bit_identical = all(D.partition_check(dist, local_rank, gt, 64, 48, 10, 5,
+                                              log=(lambda m: print(m, file=sys.stderr)) if rank == 0 else None)
+                            for gt in ("simple_lat_lon", "gaussian_islands"))
 
     if world > 1:
         from gb25_b200 import distributed as D
@@ -340,33 +406,43 @@ def main():
     pool = kernels if any(k in KERNEL_BYTES_PER_CELL for k in kernels) else stages
     dom = max((k for k in pool if k in KERNEL_BYTES_PER_CELL), key=lambda k: pool[k][0], default=None)
     roofline = None
+    traffic_tab, traffic_src = ncu_traffic()
     if dom:
         ms, calls = pool[dom]
         per_call_s = ms * 1e-3 / max(calls, 1)
         achieved = KERNEL_BYTES_PER_CELL[dom] * cells_per_rank / per_call_s / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                     "frac": achieved / hbm,
-                    "traffic": (NCU_TRAFFIC_BYTES.get(dom) if args.workload == "tripolar_quarter_degree" and world == 1 else None),
+                    "traffic": (traffic_tab.get(dom[7:], {}).get("dram_bytes") if args.workload == "tripolar_quarter_degree" else None),
+                    "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": KERNEL_BYTES_PER_CELL[dom] * cells_per_rank, "peak_source": peak_src,
                     "avg_launch_ms": per_call_s * 1e3, "share_of_step": ms / tot_ms,
                     "whole_step": {"algorithmic_bytes_per_cell_step": ALGORITHMIC_BYTES_PER_CELL_STEP,
+                                   "traffic": (traffic_tab.get("__step__", {}).get("dram_bytes")
+                                               if args.workload == "tripolar_quarter_degree" else None),
                                    "achieved": ALGORITHMIC_BYTES_PER_CELL_STEP * value / world / 1e9,
                                    "frac": ALGORITHMIC_BYTES_PER_CELL_STEP * value / world / 1e9 / hbm},
                     "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
                     "kernel_ms_per_launch": {k[7:]: v[0] / max(v[1], 1) for k, v in kernels.items()}}
     line = {"metric": "cell_steps_per_s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+            "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "grid": grid_type, "Nx_per_gpu": Nx, "Ny_per_gpu": Ny, "Nz": Nz, "dt": dt,
                        "partition": [Rx, Ry], "halo": 8, "substeps": 30, "l2": "inputs larger than L2 (each 3-D field is 226 MB)"
                        if Nx * Ny * Nz * 4 > 126e6 else "working set fits in L2: latency-bound config",
                        "state_finite": finite},
+            "multi_gpu_bit_identical": bit_identical,
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(args.workload)
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
+    if not finite:
+        raise SystemExit("bench.py: the model state is not finite after the timed region")
+    if bit_identical is False:
+        raise SystemExit("bench.py: the partitioned run differs from the single-GPU run (partition_check)")
 
 
 if __name__ == "__main__":

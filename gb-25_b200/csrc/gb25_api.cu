@@ -201,7 +201,6 @@ extern "C" int gb25_destroy(gb25_handle* h) {
   tma_free(h);
   baro_plan_free(h);
   for (void* p : h->allocs) cudaFree(p);
-  if (h->stage_dev) cudaFree(h->stage_dev);
   for (auto& s : h->timers) for (auto& e : s.ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   if (h->loop_start) cudaEventDestroy(h->loop_start);
   if (h->loop_stop) cudaEventDestroy(h->loop_stop);
@@ -333,11 +332,6 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
   f.feta = h->field_ptr[GB25_FILT_ETA]; f.fu = h->field_ptr[GB25_FILT_U]; f.fv = h->field_ptr[GB25_FILT_V];
   f.gU = h->field_ptr[GB25_GN_BARO_U]; f.gV = h->field_ptr[GB25_GN_BARO_V];
   f.gmU = h->field_ptr[GB25_GM_BARO_U]; f.gmV = h->field_ptr[GB25_GM_BARO_V];
-  h->stage_elems = n3;
-  {
-    cudaError_t ce = cudaMalloc(&h->stage_dev, n3 * sizeof(float));
-    if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc staging: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
-  }
   CKC(ckcuda(cudaStreamSynchronize(h->stream), "create sync"));
 #undef CKC
   *out = h;

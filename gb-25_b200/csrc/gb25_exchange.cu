@@ -229,6 +229,10 @@ void exchange_baro_eta(Handle* h) {   // after the eta kernel: the U,V kernel re
   if (c.Rx > 1) { mask_out |= 1 << SLOT_E; mask_in |= 1 << SLOT_W; }
   if (c.ry < c.Ry - 1) mask_out |= 1 << SLOT_N;
   if (c.ry > 0) mask_in |= 1 << SLOT_S;
+  // Fold partners acknowledge each other here: k_baro_uv(m+1) of the partner stores -V into MY row Ny+1, which my
+  // k_baro_eta(m+1) (just finished) had to read with the substep-m value.  The partner is not my x neighbour when
+  // Rx >= 4, so without this handshake nothing orders its next store after my read.
+  if (c.topo_y == GB25_TOPO_FOLD && c.ry == c.Ry - 1 && c.Rx > 1) { mask_out |= 1 << SLOT_FOLD; mask_in |= 1 << SLOT_FOLD; }
   if (mask_out | mask_in) { X.seq++; signal_slots(h, mask_out); wait_slots(h, mask_in); }
 }
 void exchange_baro_uv(Handle* h) {    // after the U,V kernel: the eta kernel reads U(i+1), V(j+1)
@@ -323,6 +327,10 @@ extern "C" int gb25_exchange_connect(gb25_handle* h, const void* blobs, int nran
     }
     X.to[s] = mapped[r];
   }
+  // A reconnect restarts every sequence number, so the flag words and the pair inbox must not keep values of the previous
+  // session (a stale number would satisfy a wait).  The caller synchronises all ranks before reconnecting and puts a
+  // barrier after it (distributed.connect), so no neighbour writes into this buffer while it is cleared.
+  if (cudaMemset(X.flags, 0, 2 << 20) != cudaSuccess) { h->err = "gb25_exchange_connect: cudaMemset flags"; return GB25_ERR_CUDA; }
   X.seq = 0;
   X.on = true;
   baro_plan_free(h);   // the persistent substep kernel restarts its sequence numbers on the (zeroed) shared flag buffer

@@ -61,9 +61,6 @@ struct gb25_handle {
   bool loop_timed = false;
   bool timers_on = false;
   std::vector<StageTimer> timers;
-  // staging for parent-shaped transfers
-  float* stage_dev = nullptr;
-  size_t stage_elems = 0;
   bool use_fused = true;
   bool use_tma = true;
   bool use_overlap = false;            // run the T,S halo fill + hydrostatic pressure on a second stream during the substeps

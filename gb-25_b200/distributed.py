@@ -109,6 +109,65 @@ def barrier(model):
     model.dist.barrier()
 
 
+def partition_check(dist, local_rank, grid_type="gaussian_islands", tx=64, ty=48, Nz=10, nsteps=5, log=None):
+    """The reference's sharded correctness protocol
+    (/root/reference/correctness/correctness_sharded_baroclinic_instability_simulation_run.jl: a sharded model against
+    an unsharded one) with a stricter criterion: the (Rx, Ry)-partitioned run over all ranks of ``dist`` must equal the
+    single-GPU run of the same global problem BIT FOR BIT (same kernels, same per-cell arithmetic; halos are copies).
+    Collective: every rank calls it; returns the same bool on every rank.  Rank 0 runs the unpartitioned model."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    Rx, Ry = factors(world)
+    gNx, gNy = tx * Rx, ty * Ry
+    m = sharded_baroclinic_instability_model(M.B200(local_rank), tx, ty, Nz, Δt=60.0, grid_type=grid_type, Rx=Rx, Ry=Ry,
+                                             rank=rank, dist=dist)
+    gg = m.global_grid
+    rng = np.random.default_rng(42)
+    T, S = _grids.baroclinic_instability_state(gg)
+    ny_v = gNy + (1 if gg.topo_y == _grids.TOPO_BOUNDED else 0)
+    state = {"T": T.astype(np.float32), "S": S.astype(np.float32),
+             "u": (1e-3 * rng.random((Nz, gNy, gNx))).astype(np.float32),
+             "v": (1e-3 * rng.random((Nz, ny_v, gNx))).astype(np.float32)}
+    for n, a in state.items():
+        scatter_interior(m, n, a)
+    barrier(m)
+    M.first_time_step(m)
+    M.time_step(m)
+    M.loop(m, nsteps - 1)        # both entry points: gb25_time_step and gb25_loop
+    barrier(m)
+    names = ("u", "v", "w", "T", "S", "eta", "Gn_u", "Gn_v", "Gn_T", "Gn_S", "Gm_u", "U", "V", "filt_U", "filt_eta")
+    got = {n: gather_interior(m, n) for n in names}
+    ok = True
+    if rank == 0:
+        ref = M.baroclinic_instability_model(M.B200(local_rank), gNx, gNy, Nz, Δt=60.0, grid_type=grid_type)
+        for n, a in state.items():
+            ref.set_interior(n, a)
+        M.first_time_step(ref)
+        M.time_step(ref)
+        M.loop(ref, nsteps - 1)
+        for n in names:
+            r = ref.interior(n)
+            g = got[n][:, :r.shape[1]]
+            r = r[:, :g.shape[1]]
+            if not np.array_equal(r.view(np.uint32), g.view(np.uint32)):
+                d = np.abs(r.astype(np.float64) - g.astype(np.float64))
+                idx = np.unravel_index(np.nanargmax(d), d.shape)
+                if log:
+                    log(f"MISMATCH {n}: max|d|={np.nanmax(d):.3e} of max {np.abs(r).max():.3e} at k,j,i={idx} "
+                        f"n={np.count_nonzero(r != g)}")
+                ok = False
+        if log:
+            log(("DIST_OK" if ok else "DIST_FAIL") + f" {grid_type} {Rx}x{Ry} tiles of {tx}x{ty}x{Nz}, {nsteps + 1} steps, "
+                f"{m.handle.launch_count()} launches on rank 0")
+        ref.close()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    m.close()
+    dist.barrier()
+    return bool(int(flag.item()))
+
+
 # ------------------------------------------------------------------------------------------------
 # Host restatement of the exchange protocol (tests only; the product moves halos inside libgb25cuda)
 # ------------------------------------------------------------------------------------------------

@@ -77,6 +77,21 @@ def _assert_close(rm, vm, names, rtol=RTOL, elementwise=None, halos=True):
     assert not bad, f"mismatch in {bad}"
 
 
+def _assert_as_close_as_f32(rm, v32, v64, names, factor=3.0, rtol=RTOL, halos=True):
+    """CUDA is as close to the Float64 oracle as the Float32 oracle is (x factor), or inside rtol of it."""
+    bad = []
+    for n in names:
+        get = (lambda m: m.parent(n)) if halos else (lambda m: m.interior(n))
+        t = get(v64).astype(np.float64)
+        nrm = max(np.linalg.norm(t), 1e-300)
+        e32 = np.linalg.norm(get(v32).astype(np.float64) - t) / nrm
+        ecu = np.linalg.norm(get(rm).astype(np.float64) - t) / nrm
+        print(f"{n:8s} |cuda-f64|={ecu:.3e}  |f32-f64|={e32:.3e}")
+        if not (np.isfinite(ecu) and ecu <= max(rtol, factor * e32)):
+            bad.append((n, ecu, e32))
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("grid_type,Nx,Ny,Nz", GRIDS)
 @pytest.mark.parametrize("state", ["zero_tracers", "baroclinic"])
 def test_operators_one_by_one(oracle_mod, grid_type, Nx, Ny, Nz, state):
@@ -98,6 +113,7 @@ def test_operators_one_by_one(oracle_mod, grid_type, Nx, Ny, Nz, state):
     _assert_close(rm, vm, ("w",), rtol=1e-5, elementwise=1e-5)
     _assert_close(rm, vm, ("p",), rtol=1e-5, elementwise=2e-5)
     resync()
+    vm_inputs = {n: vm.parent(n) for n in STATE_FIELDS}       # the inputs of the tendency operators
     M.compute_interior_tracer_tendencies_workload(vm); M.compute_interior_tracer_tendencies_workload(rm)
     M.compute_interior_momentum_tendencies_workload(vm); M.compute_interior_momentum_tendencies_workload(rm)
     if state == "zero_tracers":
@@ -105,7 +121,15 @@ def test_operators_one_by_one(oracle_mod, grid_type, Nx, Ny, Nz, state):
         _assert_close(rm, vm, ("Gn_u", "Gn_v"), elementwise=ew)
     else:
         _assert_close(rm, vm, ("Gn_v", "Gn_T", "Gn_S"))
-        _assert_close(rm, vm, ("Gn_u",), rtol=5e-2)      # Float32 noise of the O(700) pressure, see module docstring
+        # Gn_u: Float32 round-off of the O(700) pressure divided by dx dominates the small zonal tendency, so the
+        # Float32 oracle is itself percent-level away from the truth there.  Criterion: the same operator applied by
+        # the Float64 oracle to the same (Float32-valued) inputs is the truth; CUDA must be as close to it as the
+        # Float32 oracle is (factor 3), or inside the reference rtol.
+        _, v64 = make_models(grid_type, Nx, Ny, Nz, 60.0, oracle_mod, dtype=np.float64, with_cuda=False, state=state)
+        for n in STATE_FIELDS:
+            v64.set_parent(n, vm_inputs[n])
+        M.compute_interior_momentum_tendencies_workload(v64)
+        _assert_as_close_as_f32(rm, vm, v64, ("Gn_u", "Gn_v"))
     resync()
     # give G- something to chew on, then the AB2 step with chi = 0.1 and the Euler variant
     for n in ("u", "v", "T", "S"):
@@ -369,6 +393,70 @@ def test_full_size_properties_tripolar_1440x600x50():
         p = a[n].copy()
         p[Hz:Hz + Nz, Hy:Hy + Ny, Hx:Hx + Nx] = 0
         assert not p.any(), f"{n}: halo of a tendency array was written"
+
+
+def _three_way(grid_type, Nx, Ny, Nz, dt, nsteps, oracle_mod):
+    """libgb25cuda, the Float32 oracle and the Float64 oracle from the benchmark's synthetic state
+    (bench.synthetic_state), first_time_step + nsteps AB2 steps each.  At these sizes the Float32 oracle evaluates
+    the smoothness indicators as sums of squares (oracle_beta_form=1): the expanded form of the recalled reference
+    hits beta + eps == 0 about once per 1e8 evaluations in Float32 and returns NaN (DESIGN.md deviation D1); the
+    Float64 oracle keeps the reference's expanded form."""
+    import bench
+    ph = PhysicsConfig(oracle_beta_form=1)
+    mk = lambda dtype, physics: M.baroclinic_instability_model(oracle_mod.CPUOracle(dtype), Nx, Ny, Nz, Δt=dt, grid_type=grid_type,
+                                                                 model_cls=oracle_mod.OracleModel, physics=physics)
+    v32, v64 = mk(np.float32, ph), mk(np.float64, None)
+    bench.synthetic_state(v32)
+    M.sync_states(v64, v32)
+    rm = M.baroclinic_instability_model(M.B200(0), Nx, Ny, Nz, Δt=dt, grid_type=grid_type)
+    M.sync_states(rm, v32)
+    for m in (rm, v32, v64):
+        M.first_time_step(m)
+        if m is rm:
+            M.loop(m, nsteps)                     # the benchmark's entry point (gb25_loop)
+        else:
+            for _ in range(nsteps):
+                M.time_step(m)
+    return rm, v32, v64
+
+
+COMPARED = ("u", "v", "w", "T", "S", "eta", "Gn_u", "Gn_v", "Gn_T", "Gn_S", "Gm_u", "Gm_v", "Gm_T", "Gm_S",
+            "filt_U", "filt_V", "filt_eta")
+
+
+def _parity_at_size(rm, v32, v64):
+    # (a) the reference's criterion (src/correctness.jl:28-90), halos included, against the Float32 oracle for every
+    #     field but the zonal momentum tendency (Float32 round-off of the O(700) pressure, see the module docstring)
+    tight = [n for n in COMPARED if n not in ("Gn_u", "Gm_u")]
+    _assert_close(rm, v32, tight, rtol=RTOL, elementwise=None)
+    # (b) every field, Gn_u included: as close to the Float64 oracle as the Float32 oracle is
+    _assert_as_close_as_f32(rm, v32, v64, COMPARED)
+    # (c) element-wise bound on the prognostic state (catches indexing mistakes the 2-norm forgives)
+    for n in ("u", "v", "T", "S", "eta"):
+        a, b = rm.parent(n).astype(np.float64), v32.parent(n).astype(np.float64)
+        assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max(), n
+
+
+def test_headline_config_against_oracle_tripolar_1440x600x50(oracle_mod):
+    """BASELINE.json configs[1] at FULL size — the configuration bench.py times — first step + 2 AB2 steps through
+    gb25_first_time_step / gb25_loop against the CPU oracle in Float32 and Float64.  Here 98.5 % of the cells take the
+    TMA fast-path kernels that are 64 % of the benchmarked step."""
+    rm, v32, v64 = _three_way("gaussian_islands", 1440, 600, 50, 60.0, 2, oracle_mod)
+    _parity_at_size(rm, v32, v64)
+    rm.close()
+
+
+def test_half_size_10_steps_against_oracle_tripolar_720x300x50(oracle_mod):
+    rm, v32, v64 = _three_way("gaussian_islands", 720, 300, 50, 60.0, 10, oracle_mod)
+    _parity_at_size(rm, v32, v64)
+    rm.close()
+
+
+def test_flat_tripolar_fast_path_against_oracle_256x128x12(oracle_mod):
+    """No bathymetry: every interior tile runs k_mom_tma_p2 / k_tracer_tma only (no generic list)."""
+    rm, v32, v64 = _three_way("tripolar", 256, 128, 12, 60.0, 5, oracle_mod)
+    _parity_at_size(rm, v32, v64)
+    rm.close()
 
 
 def test_full_size_free_surface_volume_conservation_latlon_1440x600x50():
