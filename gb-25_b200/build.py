@@ -32,6 +32,30 @@ def _newer(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
+def build_variant(suffix, defines, verbose=False):
+    """Experiment build: libgb25cuda<suffix>.so compiled with extra -D flags, objects in a private directory."""
+    nvcc = _nvcc()
+    odir = os.path.join(CSRC, "build", suffix.strip("_") or "default")
+    os.makedirs(odir, exist_ok=True)
+    lib = os.path.join(CSRC, f"libgb25cuda{suffix}.so")
+    objs, procs = [], []
+    for s in CU_SOURCES:
+        o = os.path.join(odir, s[:-3] + ".o")
+        objs.append(o)
+        cmd = [nvcc, *[f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")], *defines, "-c", os.path.join(CSRC, s), "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    subprocess.check_call([nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib
+
+
 def build_cuda(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s))]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
@@ -60,4 +84,8 @@ def build_cuda(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--suffix" in sys.argv:      # python -m gb25_b200.build --suffix _x -DFOO=1 -DBAR=2
+        q = sys.argv.index("--suffix")
+        print(build_variant(sys.argv[q + 1], [a for a in sys.argv[q + 2:] if a.startswith("-D")], verbose="-v" in sys.argv))
+    else:
+        print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))

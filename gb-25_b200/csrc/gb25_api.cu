@@ -298,13 +298,22 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     CKC(ckcuda(cudaMemsetAsync(d, 0, n * sizeof(float), h->stream), "cudaMemset"));
     h->field_ptr[fidx] = d;
   }
+  for (int q = 0; q < 4; q++) {
+    static const int ids[4] = {GB25_U, GB25_V, GB25_T, GB25_S};
+    h->state_buf[0][q] = h->field_ptr[ids[q]];
+    cudaError_t ce = cudaMalloc(&h->state_buf[1][q], n3 * sizeof(float));
+    if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc state buffer: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
+    h->allocs.push_back(h->state_buf[1][q]);
+    CKC(ckcuda(cudaMemsetAsync(h->state_buf[1][q], 0, n3 * sizeof(float), h->stream), "cudaMemset"));
+  }
   for (float** sp : {&h->zeta, &h->dxU, &h->dyV}) {
     cudaError_t ce = cudaMalloc(sp, n3 * sizeof(float));
     if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc scratch: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
     h->allocs.push_back(*sp);
     CKC(ckcuda(cudaMemsetAsync(*sp, 0, n3 * sizeof(float), h->stream), "cudaMemset"));
   }
-  for (float** sp : {&h->us2, &h->vs2, &h->corr_u, &h->corr_v, &h->carry[0], &h->carry[1], &h->carry[2], &h->carry[3]}) {
+  for (float** sp : {&h->us2, &h->vs2, &h->corr_u, &h->corr_v, &h->carry[0], &h->carry[1], &h->carry[2], &h->carry[3],
+                     &h->spec2d[0], &h->spec2d[1], &h->spec2d[2], &h->spec2d[3]}) {
     cudaError_t ce = cudaMalloc(sp, n2 * sizeof(float));
     if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc scratch: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
     h->allocs.push_back(*sp);
@@ -315,8 +324,8 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     h->use_fused = !(e && e[0] == '0');
     const char* t = getenv("GB25_TMA");
     h->use_tma = !(t && t[0] == '0');
-    const char* ov = getenv("GB25_OVERLAP");
-    h->use_overlap = (ov && ov[0] == '1');   // measured: 5.33 vs 5.36 ms/step at C2 — within noise, so off by default
+    const char* sp = getenv("GB25_SPECULATE");
+    h->use_spec = !(sp && sp[0] == '0');
     const char* pk = getenv("GB25_PACKED");
     h->use_packed = !(pk && pk[0] == '0');
     const char* tt = getenv("GB25_TMA_TRACER");
@@ -344,7 +353,7 @@ extern "C" int gb25_field_shape(const gb25_handle* h, int field, int shape[3]) {
   parent_shape(h, field, shape);
   return GB25_OK;
 }
-static int copy_field(Handle* h, int field, float* host, bool to_device) {
+static int copy_field(Handle* h, int field, float* host, bool to_device, bool sync = true) {
   if (field < 0 || field >= GB25_FIELD_COUNT || !host) { h->err = "bad field id or null buffer"; return GB25_ERR_INVALID; }
   int s[3];
   parent_shape(h, field, s);
@@ -356,7 +365,17 @@ static int copy_field(Handle* h, int field, float* host, bool to_device) {
   if (to_device) { p.srcPtr = hp; p.dstPtr = dp; p.kind = cudaMemcpyHostToDevice; }
   else { p.srcPtr = dp; p.dstPtr = hp; p.kind = cudaMemcpyDeviceToHost; }
   CK(h, cudaMemcpy3DAsync(&p, h->stream));
-  CK(h, cudaStreamSynchronize(h->stream));
+  if (to_device) {
+    h->spec.valid = false;
+    // the other half of a double-buffered field receives the same parent, so that halo cells no fill ever writes
+    // (y-z corners, the rows behind an impenetrable wall) hold the uploaded values whichever buffer is current
+    for (int q = 0; q < 4; q++)
+      if (h->field_ptr[field] == h->state_buf[h->parity][q]) {
+        p.dstPtr = make_cudaPitchedPtr(h->state_buf[1 - h->parity][q], (size_t)g.PX * sizeof(float), g.PX, g.PY);
+        CK(h, cudaMemcpy3DAsync(&p, h->stream));
+      }
+  }
+  if (sync) CK(h, cudaStreamSynchronize(h->stream));
   return GB25_OK;
 }
 extern "C" int gb25_set_field(gb25_handle* h, int field, const float* host_parent) {
@@ -415,9 +434,9 @@ static void stage_aux(Handle* h) {
   else { StageScope t(h, "compute_w_from_continuity"); launch_compute_w(h); }
   { StageScope t(h, "update_hydrostatic_pressure"); launch_compute_p(h); }
 }
-static void stage_tend(Handle* h) {
-  { StageScope t(h, "momentum_tendencies"); launch_momentum_tendency(h); }
-  { StageScope t(h, "tracer_tendencies"); launch_tracer_tendency(h); }
+static void stage_tend(Handle* h, const Ab2Spec* spec = nullptr) {
+  { StageScope t(h, "momentum_tendencies"); launch_momentum_tendency(h, spec); }
+  { StageScope t(h, "tracer_tendencies"); launch_tracer_tendency(h, spec); }
   if (h->cfg.closure == 1) { StageScope t(h, "vertical_diffusion"); launch_vdiff_explicit(h); }
 }
 static void stage_update_state(Handle* h) {
@@ -447,40 +466,28 @@ static void stage_initialize(Handle* h) {
   HaloSpec sb[2] = {{h->f.bu, 1, 0, 0, -1.f}, {h->f.bv, 0, 1, 0, -1.f}};
   launch_fill_halo(h, sb, 2, false);
 }
-struct StreamSwap {   // launch on another stream for the lifetime of the object
-  Handle* h; cudaStream_t saved;
-  StreamSwap(Handle* h_, cudaStream_t s) : h(h_), saved(h_->stream) { h->stream = s; }
-  ~StreamSwap() { h->stream = saved; }
-};
+static void swap_state_buffers(Handle* h) {
+  static const int ids[4] = {GB25_U, GB25_V, GB25_T, GB25_S};
+  h->parity ^= 1;
+  DevFields& f = h->f;
+  f.u = h->state_buf[h->parity][0]; f.v = h->state_buf[h->parity][1]; f.T = h->state_buf[h->parity][2]; f.S = h->state_buf[h->parity][3];
+  for (int q = 0; q < 4; q++) h->field_ptr[ids[q]] = h->state_buf[h->parity][q];
+}
 // fused step path: identical results, fewer passes over the 3-D state (see gb25_kernels.cu "Fused step path")
 static void one_time_step_fused(Handle* h, float dt, float chi) {
   DevFields& f = h->f;
-  { StageScope t(h, "ab2_step_fields"); launch_ab2_fused(h, dt, chi); }
+  if (h->spec.valid && h->spec.dt == dt && h->spec.chi == chi) {
+    // the tendency kernels of the previous step already wrote u*, v*, T', S' (masked) into the other state buffers and
+    // GU, GV, sum dz u*, sum dz v* into their 2-D arrays: the AB2 stage is a pointer swap
+    StageScope t(h, "ab2_step_fields");
+    swap_state_buffers(h);
+    launch_commit_spec(h);
+  } else {
+    StageScope t(h, "ab2_step_fields"); launch_ab2_fused(h, dt, chi);
+  }
+  h->spec.valid = false;
   if (h->cfg.closure == 2) { StageScope t(h, "vertical_diffusion"); launch_implicit_columns(h, dt, true); }
-  // T and S are final once the AB2 update (and the implicit solve) are done: their halo fill and the hydrostatic
-  // pressure scan do not depend on the barotropic solve, so they run on a second stream underneath the 43 small,
-  // L2-bound substep kernels (single-tile handles only: the tile exchange numbers its phases on one stream).
-  const bool overlap = h->use_overlap && !h->ex.on;
-  if (overlap) {
-    cudaEventRecord(h->ev_fork, h->stream);
-    cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
-    StreamSwap sw(h, h->stream2);
-    { StageScope t(h, "fill_halo_regions_TS"); HaloSpec s3[2] = {{f.T, 0, 0, 0, 1.f}, {f.S, 0, 0, 0, 1.f}}; launch_fill_halo(h, s3, 2, true); }
-    { StageScope t(h, "update_hydrostatic_pressure"); launch_compute_p(h); }
-    cudaEventRecord(h->ev_join, h->stream2);
-  }
-  {
-    StageScope t(h, "split_explicit_free_surface");
-    if (overlap) {   // (the second-stream variant keeps the reference's fill points)
-      HaloSpec sg[2] = {{f.gU, 1, 0, 0, -1.f}, {f.gV, 0, 1, 0, -1.f}};
-      launch_fill_halo(h, sg, 2, false);
-    }
-    launch_barotropic(h, dt);
-    if (overlap) {
-      HaloSpec sb[2] = {{f.bu, 1, 0, 0, -1.f}, {f.bv, 0, 1, 0, -1.f}};
-      launch_fill_halo(h, sb, 2, false);
-    }
-  }
+  { StageScope t(h, "split_explicit_free_surface"); launch_barotropic(h, dt); }
   h->time += (double)dt; h->iteration += 1; h->last_dt = dt;
   { StageScope t(h, "correct_velocities_and_cache"); launch_correct_fused(h); }
   // G- <- Gn: swap the buffers; the tendency kernels below overwrite the whole interior of the new Gn,
@@ -489,21 +496,15 @@ static void one_time_step_fused(Handle* h, float dt, float chi) {
     std::swap(f.gn[q], f.gm[q]);
     std::swap(h->field_ptr[GB25_GN_U + q], h->field_ptr[GB25_GM_U + q]);
   }
-  if (overlap) {
-    {
-      StageScope t(h, "fill_halo_regions");
-      HaloSpec s3[2] = {{f.u, 1, 0, 0, -1.f}, {f.v, 0, 1, 0, -1.f}};
-      launch_fill_halo(h, s3, 2, true);
-      HaloSpec s2[3] = {{f.eta, 0, 0, 1, 1.f}, {f.bu, 1, 0, 0, -1.f}, {f.bv, 0, 1, 0, -1.f}};
-      launch_fill_halo(h, s2, 3, false);
-    }
-    { StageScope t(h, "compute_w_from_continuity"); launch_aux_columns(h); }
-    cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+  fill_prognostic_fused(h);
+  stage_aux(h);
+  if (spec_possible(h)) {
+    const Ab2Spec sp = {dt, 1.5f + h->cfg.chi, 0.5f + h->cfg.chi};
+    stage_tend(h, &sp);
+    h->spec.valid = true; h->spec.dt = dt; h->spec.chi = h->cfg.chi;
   } else {
-    fill_prognostic_fused(h);
-    stage_aux(h);
+    stage_tend(h);
   }
-  stage_tend(h);
 }
 static void one_time_step(Handle* h, float dt, bool euler) {
   euler = euler || (dt != h->last_dt);
@@ -515,11 +516,12 @@ static void one_time_step(Handle* h, float dt, bool euler) {
   stage_update_state(h);
 }
 
-extern "C" int gb25_initialize(gb25_handle* h) { REQUIRE(h); stage_initialize(h); return check_async(h, "gb25_initialize"); }
-extern "C" int gb25_update_state(gb25_handle* h) { REQUIRE(h); stage_update_state(h); return check_async(h, "gb25_update_state"); }
+extern "C" int gb25_initialize(gb25_handle* h) { REQUIRE(h); h->spec.valid = false; stage_initialize(h); return check_async(h, "gb25_initialize"); }
+extern "C" int gb25_update_state(gb25_handle* h) { REQUIRE(h); h->spec.valid = false; stage_update_state(h); return check_async(h, "gb25_update_state"); }
 extern "C" int gb25_first_time_step(gb25_handle* h, float dt) {
   REQUIRE(h);
   if (dt <= 0.f) dt = h->last_dt;
+  h->spec.valid = false;
   stage_initialize(h);
   stage_update_state(h);
   one_time_step(h, dt, true);
@@ -541,28 +543,32 @@ extern "C" int gb25_loop(gb25_handle* h, float dt, int nsteps) {
   h->loop_timed = true;
   return check_async(h, "gb25_loop");
 }
-extern "C" int gb25_mask_immersed_fields(gb25_handle* h) { REQUIRE(h); stage_mask(h); return check_async(h, "gb25_mask_immersed_fields"); }
-extern "C" int gb25_fill_halo_regions(gb25_handle* h) { REQUIRE(h); fill_prognostic(h); return check_async(h, "gb25_fill_halo_regions"); }
-extern "C" int gb25_compute_auxiliaries(gb25_handle* h) { REQUIRE(h); stage_aux(h); return check_async(h, "gb25_compute_auxiliaries"); }
-extern "C" int gb25_compute_tendencies(gb25_handle* h) { REQUIRE(h); stage_tend(h); return check_async(h, "gb25_compute_tendencies"); }
+extern "C" int gb25_mask_immersed_fields(gb25_handle* h) { REQUIRE(h); h->spec.valid = false; stage_mask(h); return check_async(h, "gb25_mask_immersed_fields"); }
+extern "C" int gb25_fill_halo_regions(gb25_handle* h) { REQUIRE(h); h->spec.valid = false; fill_prognostic(h); return check_async(h, "gb25_fill_halo_regions"); }
+extern "C" int gb25_compute_auxiliaries(gb25_handle* h) { REQUIRE(h); h->spec.valid = false; stage_aux(h); return check_async(h, "gb25_compute_auxiliaries"); }
+extern "C" int gb25_compute_tendencies(gb25_handle* h) { REQUIRE(h); h->spec.valid = false; stage_tend(h); return check_async(h, "gb25_compute_tendencies"); }
 extern "C" int gb25_compute_momentum_tendencies(gb25_handle* h) {
   REQUIRE(h);
+  h->spec.valid = false;
   { StageScope t(h, "momentum_tendencies"); launch_momentum_tendency(h); }
   return check_async(h, "gb25_compute_momentum_tendencies");
 }
 extern "C" int gb25_compute_tracer_tendencies(gb25_handle* h) {
   REQUIRE(h);
+  h->spec.valid = false;
   { StageScope t(h, "tracer_tendencies"); launch_tracer_tendency(h); }
   return check_async(h, "gb25_compute_tracer_tendencies");
 }
 extern "C" int gb25_ab2_step(gb25_handle* h, float dt, float chi) {
   REQUIRE(h);
+  h->spec.valid = false;
   if (dt <= 0.f) dt = h->last_dt;
   stage_ab2(h, dt, chi);
   return check_async(h, "gb25_ab2_step");
 }
 extern "C" int gb25_correct_velocities_and_cache_previous_tendencies(gb25_handle* h) {
   REQUIRE(h);
+  h->spec.valid = false;
   stage_correct(h);
   return check_async(h, "gb25_correct_velocities_and_cache_previous_tendencies");
 }

@@ -94,9 +94,15 @@ __global__ void k_wait(volatile int* flags, int mask, int val) {
 }
 
 // --------------------------------------------------------------------------------- host side
-static int ex_field_id(Handle* h, const float* a) {
+void exchange_table(Handle* h, float* tab[EX_NF]) {
   const DevFields& f = h->f;
-  const float* tab[EX_NF] = {f.u, f.v, f.T, f.S, f.eta, f.bu, f.bv, f.gU, f.gV};
+  float* t[EX_NF] = {h->state_buf[0][0], h->state_buf[0][1], h->state_buf[0][2], h->state_buf[0][3], f.eta, f.bu, f.bv, f.gU, f.gV,
+                     h->state_buf[1][0], h->state_buf[1][1], h->state_buf[1][2], h->state_buf[1][3]};
+  for (int q = 0; q < EX_NF; q++) tab[q] = t[q];
+}
+static int ex_field_id(Handle* h, const float* a) {
+  float* tab[EX_NF];
+  exchange_table(h, tab);
   for (int q = 0; q < EX_NF; q++) if (tab[q] == a) return q;
   return -1;
 }
@@ -259,8 +265,8 @@ extern "C" int gb25_exchange_export(gb25_handle* h, void* blob) {
     if (cudaMalloc(&X.flags, 2 << 20) != cudaSuccess) { h->err = "gb25_exchange_export: cudaMalloc flags"; return GB25_ERR_ALLOC; }
     cudaMemset(X.flags, 0, 2 << 20);
   }
-  const DevFields& f = h->f;
-  float* tab[EX_NF] = {f.u, f.v, f.T, f.S, f.eta, f.bu, f.bv, f.gU, f.gV};
+  float* tab[EX_NF];
+  exchange_table(h, tab);
   for (int q = 0; q < EX_NF; q++) {
     cudaError_t e = cudaIpcGetMemHandle(&b.fld[q], tab[q]);
     if (e != cudaSuccess) { h->err = std::string("gb25_exchange_export: cudaIpcGetMemHandle: ") + cudaGetErrorString(e); return GB25_ERR_COMM; }
@@ -300,8 +306,8 @@ extern "C" int gb25_exchange_connect(gb25_handle* h, const void* blobs, int nran
   // map every distinct peer once
   std::vector<ExPeer> mapped(nranks);
   std::vector<char> have(nranks, 0);
-  const DevFields& f = h->f;
-  float* mine[EX_NF] = {f.u, f.v, f.T, f.S, f.eta, f.bu, f.bv, f.gU, f.gV};
+  float* mine[EX_NF];
+  exchange_table(h, mine);
   for (int s = 0; s < EX_NSLOT; s++) {
     const int r = want[s];
     X.to[s].rank = r;

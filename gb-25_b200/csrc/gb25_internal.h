@@ -11,7 +11,9 @@
 struct HaloSpec { float* a; int lx, ly, lz; float sign; int flat; };   // flat = 1: a 2-D field riding in a batch of 3-D fields
 
 // ---- multi-GPU halo exchange over peer-mapped (CUDA IPC) memory, one process per GPU (gb25_exchange.cu)
-enum ExField { EX_U = 0, EX_V, EX_T, EX_S, EX_ETA, EX_BU, EX_BV, EX_GU, EX_GV, EX_NF };
+// exported allocations: both halves of the double-buffered 3-D state (all tiles flip in lockstep, so a tile's current
+// buffer always faces its neighbours' current buffers) and the 2-D fields
+enum ExField { EX_U = 0, EX_V, EX_T, EX_S, EX_ETA, EX_BU, EX_BV, EX_GU, EX_GV, EX_U2, EX_V2, EX_T2, EX_S2, EX_NF };
 enum ExSlot { SLOT_W = 0, SLOT_E, SLOT_S, SLOT_N, SLOT_FOLD, SLOT_FOLD2, EX_NSLOT };
 struct ExPeer { float* fld[EX_NF]; int* flags; int rank; };
 struct Exchange {
@@ -47,6 +49,16 @@ struct gb25_handle {
   float *us2 = nullptr, *vs2 = nullptr;   // 2-D: column sums of the AB2-updated, masked velocities (fused path)
   float *corr_u = nullptr, *corr_v = nullptr;   // 2-D: unmasked barotropic transports for the streamed corrector
   float* carry[4] = {nullptr, nullptr, nullptr, nullptr};   // 2-D: vertical flux through the top face of the topmost generic cell (u, v, T, S)
+  // Double-buffered prognostic 3-D state.  The tendency kernels that end a step can apply the AB2 update of the NEXT step in
+  // their epilogue (same dt, chi = cfg.chi): they read the state from state_buf[parity] and write the updated, masked state
+  // into state_buf[1 - parity] (neighbouring tiles still read the old one), together with the column sums the barotropic
+  // solve and the corrector need.  The next gb25_time_step with matching (dt, chi) then starts with a pointer swap instead of
+  // the AB2 pass; anything else (another dt, an upload, an operator-level call) discards the speculation.
+  float* state_buf[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // [parity][u, v, T, S]
+  int parity = 0;
+  float* spec2d[4] = {nullptr, nullptr, nullptr, nullptr};   // speculative GU, GV, sum dz u*, sum dz v* (committed by launch_commit_spec)
+  struct { bool valid = false; float dt = 0.f, chi = 0.f; } spec;
+  bool use_spec = true;
   // clock (model.clock)
   double time = 0.0;
   long iteration = 0;
@@ -63,7 +75,6 @@ struct gb25_handle {
   std::vector<StageTimer> timers;
   bool use_fused = true;
   bool use_tma = true;
-  bool use_overlap = false;            // run the T,S halo fill + hydrostatic pressure on a second stream during the substeps
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool use_tma_tracer = true;
@@ -95,6 +106,9 @@ struct StageScope {
   ~StageScope() { if (t) cudaEventRecord(t->ev[slot].second, h->stream); }
 };
 
+struct Ab2Spec { float dt, c1, c2; };   // AB2 epilogue of the tendency kernels: psi' = psi + dt (c1 Gn - c2 G-)
+bool spec_possible(Handle* h);          // gb25_kernels.cu: the configuration runs the kernels that have the epilogue
+
 // stage launchers (gb25_kernels.cu)
 void launch_fill_halo(Handle* h, const HaloSpec* specs, int n, bool three_d);
 void launch_halo_south_north(Handle* h, const HaloSpec* specs, int n, bool three_d, int mode_s, int mode_n);
@@ -105,26 +119,28 @@ void exchange_baro_eta(Handle* h);
 void exchange_baro_uv(Handle* h);
 int exchange_check_timeout(Handle* h);
 void exchange_close(Handle* h);
+void exchange_table(Handle* h, float* tab[EX_NF]);   // the allocations behind ExField, in order
 void launch_mask(Handle* h, bool uv_only);
 void launch_compute_w(Handle* h);
 void launch_compute_p(Handle* h);
-void launch_tracer_tendency(Handle* h);
+void launch_tracer_tendency(Handle* h, const Ab2Spec* spec = nullptr);
 void launch_tracer_tendency_v1(Handle* h);
 void launch_tracer_tendency_v2(Handle* h);   // gb25_tend_v2.cu
 void launch_momentum_tendency_v1(Handle* h);
 void launch_momentum_tendency_v2(Handle* h);  // gb25_tend_v2.cu
 void launch_aux_columns(Handle* h);
 void launch_generic_list(Handle* h, bool momentum, bool tracers);   // gb25_tend_v2.cu
-void launch_momentum_tendency_tma(Handle* h);   // gb25_tend_tma.cu
+void launch_momentum_tendency_tma(Handle* h, const Ab2Spec* spec = nullptr);   // gb25_tend_tma.cu
 bool tma_available(Handle* h);
-void launch_tracer_tendency_tma(Handle* h);
+void launch_tracer_tendency_tma(Handle* h, const Ab2Spec* spec = nullptr);
 void tma_free(Handle* h);           // gb25_tend_v2.cu: w + zeta + flux divergences in one column pass
-void launch_momentum_tendency(Handle* h);
+void launch_momentum_tendency(Handle* h, const Ab2Spec* spec = nullptr);
 void launch_ab2_columns(Handle* h, float dt, float chi);
 void launch_barotropic(Handle* h, float dt);
 void launch_correct_cache(Handle* h);
 void launch_barotropic_mode(Handle* h);
 void launch_ab2_fused(Handle* h, float dt, float chi);
+void launch_commit_spec(Handle* h);
 void launch_correct_fused(Handle* h);
 void launch_vdiff_explicit(Handle* h);
 void launch_implicit_columns(Handle* h, float dt, bool with_sums);

@@ -348,8 +348,12 @@ void launch_tracer_tendency_v1(Handle* h) {
   k_tracer_tendency<<<gr, b, 0, h->stream>>>(g, h->f.u, h->f.v, h->f.w, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3]);
   h->count_launch();
 }
-void launch_tracer_tendency(Handle* h) {
-  if (h->use_fused && h->use_tma && h->use_tma_tracer && h->g.Nx % 4 == 0 && tma_available(h)) { launch_generic_list(h, false, true); launch_tracer_tendency_tma(h); }
+bool spec_possible(Handle* h) {
+  return h->use_spec && h->use_fused && h->use_tma && h->use_tma_tracer && h->use_packed && h->g.Nx % 4 == 0 && h->cfg.closure != 1 &&
+         tma_available(h);
+}
+void launch_tracer_tendency(Handle* h, const Ab2Spec* spec) {
+  if (h->use_fused && h->use_tma && h->use_tma_tracer && h->g.Nx % 4 == 0 && tma_available(h)) { launch_generic_list(h, false, true); launch_tracer_tendency_tma(h, spec); }
   else if (h->use_fused && h->g.Nx % 4 == 0) { launch_generic_list(h, false, true); launch_tracer_tendency_v2(h); }
   else launch_tracer_tendency_v1(h);
 }
@@ -370,8 +374,8 @@ void launch_momentum_tendency_v1(Handle* h) {
   k_momentum_tendency<1><<<gr, b, 0, h->stream>>>(g, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[1]); h->count_launch();
 }
 
-void launch_momentum_tendency(Handle* h) {
-  if (h->use_fused && h->use_tma && h->g.Nx % 4 == 0 && tma_available(h)) { launch_generic_list(h, true, false); launch_momentum_tendency_tma(h); }
+void launch_momentum_tendency(Handle* h, const Ab2Spec* spec) {
+  if (h->use_fused && h->use_tma && h->g.Nx % 4 == 0 && tma_available(h)) { launch_generic_list(h, true, false); launch_momentum_tendency_tma(h, spec); }
   else if (h->use_fused && h->g.Nx % 2 == 0) { launch_generic_list(h, true, false); launch_momentum_tendency_v2(h); }
   else launch_momentum_tendency_v1(h);
 }
@@ -384,24 +388,23 @@ __global__ void k_ab2_columns(DevGrid g, DevFields f, float dt, float chi) {
   if (i > g.Nx) return;
   const int q2 = id2(g, i, j), n2 = g.n2;
   const float c1 = 1.5f + chi, c2 = 0.5f + chi;
-  const float ne = (chi != -0.5f) ? 1.f : 0.f;
   const int kb0 = g.kb[q2], kbw = g.kb[q2 - 1], kbs = g.kb[q2 - g.PX];
   const bool ywall = y_outside(g, j) || y_outside(g, j - 1);
   float su = 0.f, sv = 0.f;
   size_t q3 = q2 + (size_t)n2 * g.Hz;
   for (int k = 1; k <= g.Nz; k++, q3 += n2) {
     const float dz = g.dzc[k + g.Hz - 1];
-    const float gu = c1 * f.gn[0][q3] - c2 * f.gm[0][q3] * ne;
-    const float gv = c1 * f.gn[1][q3] - c2 * f.gm[1][q3] * ne;
+    const float gu = ab2_g(c1, c2, f.gn[0][q3], f.gm[0][q3]);
+    const float gv = ab2_g(c1, c2, f.gn[1][q3], f.gm[1][q3]);
     const bool pu = k <= kb0 || k <= kbw;
     const bool pv = ywall || k <= kb0 || k <= kbs;
-    const float tu = dz * (pu ? 0.f : gu), tv = dz * (pv ? 0.f : gv);
-    su = (k == 1) ? tu : su + tu;
-    sv = (k == 1) ? tv : sv + tv;
-    f.u[q3] += dt * gu;
-    f.v[q3] += dt * gv;
-    f.T[q3] = f.T[q3] + dt * (c1 * f.gn[2][q3] - c2 * f.gm[2][q3]);
-    f.S[q3] = f.S[q3] + dt * (c1 * f.gn[3][q3] - c2 * f.gm[3][q3]);
+    const float tu = __fmul_rn(dz, pu ? 0.f : gu), tv = __fmul_rn(dz, pv ? 0.f : gv);
+    su = (k == 1) ? tu : __fadd_rn(su, tu);
+    sv = (k == 1) ? tv : __fadd_rn(sv, tv);
+    f.u[q3] = ab2_upd(f.u[q3], dt, gu);
+    f.v[q3] = ab2_upd(f.v[q3], dt, gv);
+    f.T[q3] = ab2_upd(f.T[q3], dt, ab2_g(c1, c2, f.gn[2][q3], f.gm[2][q3]));
+    f.S[q3] = ab2_upd(f.S[q3], dt, ab2_g(c1, c2, f.gn[3][q3], f.gm[3][q3]));
   }
   f.gU[q2] = su; f.gV[q2] = sv;
 }
@@ -560,7 +563,6 @@ __global__ void k_ab2_fused(DevGrid g, DevFields f, float* __restrict__ us2, flo
   if (i > g.Nx) return;
   const int q2 = id2(g, i, j), n2 = g.n2;
   const float c1 = 1.5f + chi, c2 = 0.5f + chi;
-  const float ne = (chi != -0.5f) ? 1.f : 0.f;
   const int kb0 = g.kb[q2], kbw = g.kb[q2 - 1], kbs = g.kb[q2 - g.PX];
   const bool ywall = y_outside(g, j) || y_outside(g, j - 1);
   const bool imm = g.immersed;
@@ -568,25 +570,25 @@ __global__ void k_ab2_fused(DevGrid g, DevFields f, float* __restrict__ us2, flo
   size_t q3 = q2 + (size_t)n2 * g.Hz;
   for (int k = 1; k <= g.Nz; k++, q3 += n2) {   // (unrolling this loop costs occupancy: 0.54 -> 0.68 ms, measured)
     const float dz = g.dzc[k + g.Hz - 1];
-    const float gu = c1 * f.gn[0][q3] - c2 * f.gm[0][q3] * ne;
-    const float gv = c1 * f.gn[1][q3] - c2 * f.gm[1][q3] * ne;
+    const float gu = ab2_g(c1, c2, f.gn[0][q3], f.gm[0][q3]);
+    const float gv = ab2_g(c1, c2, f.gn[1][q3], f.gm[1][q3]);
     const bool pu = k <= kb0 || k <= kbw;
     const bool pv = ywall || k <= kb0 || k <= kbs;
-    const float tu = dz * (pu ? 0.f : gu), tv = dz * (pv ? 0.f : gv);
-    su = (k == 1) ? tu : su + tu;
-    sv = (k == 1) ? tv : sv + tv;
-    float un = f.u[q3] + dt * gu, vn = f.v[q3] + dt * gv;
-    float Tn = f.T[q3] + dt * (c1 * f.gn[2][q3] - c2 * f.gm[2][q3]);
-    float Sn = f.S[q3] + dt * (c1 * f.gn[3][q3] - c2 * f.gm[3][q3]);
+    const float tu = __fmul_rn(dz, pu ? 0.f : gu), tv = __fmul_rn(dz, pv ? 0.f : gv);
+    su = (k == 1) ? tu : __fadd_rn(su, tu);
+    sv = (k == 1) ? tv : __fadd_rn(sv, tv);
+    float un = ab2_upd(f.u[q3], dt, gu), vn = ab2_upd(f.v[q3], dt, gv);
+    float Tn = ab2_upd(f.T[q3], dt, ab2_g(c1, c2, f.gn[2][q3], f.gm[2][q3]));
+    float Sn = ab2_upd(f.S[q3], dt, ab2_g(c1, c2, f.gn[3][q3], f.gm[3][q3]));
     if (imm) {
       if (pu) un = 0.f;
       if (pv) vn = 0.f;
       if (k <= kb0) { Tn = 0.f; Sn = 0.f; }
     }
     f.u[q3] = un; f.v[q3] = vn; f.T[q3] = Tn; f.S[q3] = Sn;
-    const float wu = dz * un, wv = dz * vn;
-    bu = (k == 1) ? wu : bu + wu;
-    bv = (k == 1) ? wv : bv + wv;
+    const float wu = __fmul_rn(dz, un), wv = __fmul_rn(dz, vn);
+    bu = (k == 1) ? wu : __fadd_rn(bu, wu);
+    bv = (k == 1) ? wv : __fadd_rn(bv, wv);
   }
   f.gU[q2] = su; f.gV[q2] = sv;
   us2[q2] = bu; vs2[q2] = bv;
@@ -625,7 +627,6 @@ __global__ void __launch_bounds__(128) k_ab2_uv(DevGrid g, DevFields f, float* _
   if (i > g.Nx) return;
   const int q2 = id2(g, i, j), n2 = g.n2;
   const float c1 = 1.5f + chi, c2 = 0.5f + chi;
-  const float ne = (chi != -0.5f) ? 1.f : 0.f;
   const int kb0 = g.kb[q2], kbw = g.kb[q2 - 1], kbs = g.kb[q2 - g.PX];
   const bool ywall = y_outside(g, j) || y_outside(g, j - 1);
   const bool imm = g.immersed;
@@ -633,22 +634,22 @@ __global__ void __launch_bounds__(128) k_ab2_uv(DevGrid g, DevFields f, float* _
   size_t q3 = q2 + (size_t)n2 * g.Hz;
   for (int k = 1; k <= g.Nz; k++, q3 += n2) {
     const float dz = g.dzc[k + g.Hz - 1];
-    const float gu = c1 * f.gn[0][q3] - c2 * f.gm[0][q3] * ne;
-    const float gv = c1 * f.gn[1][q3] - c2 * f.gm[1][q3] * ne;
+    const float gu = ab2_g(c1, c2, f.gn[0][q3], f.gm[0][q3]);
+    const float gv = ab2_g(c1, c2, f.gn[1][q3], f.gm[1][q3]);
     const bool pu = k <= kb0 || k <= kbw;
     const bool pv = ywall || k <= kb0 || k <= kbs;
-    const float tu = dz * (pu ? 0.f : gu), tv = dz * (pv ? 0.f : gv);
-    su = (k == 1) ? tu : su + tu;
-    sv = (k == 1) ? tv : sv + tv;
-    float un = f.u[q3] + dt * gu, vn = f.v[q3] + dt * gv;
+    const float tu = __fmul_rn(dz, pu ? 0.f : gu), tv = __fmul_rn(dz, pv ? 0.f : gv);
+    su = (k == 1) ? tu : __fadd_rn(su, tu);
+    sv = (k == 1) ? tv : __fadd_rn(sv, tv);
+    float un = ab2_upd(f.u[q3], dt, gu), vn = ab2_upd(f.v[q3], dt, gv);
     if (imm) {
       if (pu) un = 0.f;
       if (pv) vn = 0.f;
     }
     f.u[q3] = un; f.v[q3] = vn;
-    const float wu = dz * un, wv = dz * vn;
-    bu = (k == 1) ? wu : bu + wu;
-    bv = (k == 1) ? wv : bv + wv;
+    const float wu = __fmul_rn(dz, un), wv = __fmul_rn(dz, vn);
+    bu = (k == 1) ? wu : __fadd_rn(bu, wu);
+    bv = (k == 1) ? wv : __fadd_rn(bv, wv);
   }
   f.gU[q2] = su; f.gV[q2] = sv;
   us2[q2] = bu; vs2[q2] = bv;
@@ -669,8 +670,8 @@ __global__ void __launch_bounds__(128) k_ab2_ts_3d(DevGrid g, DevFields f, float
       float* __restrict__ x = q == 2 ? f.T : f.S;
       const float4 x4 = *reinterpret_cast<const float4*>(x + q3);
       const float4 n4 = *reinterpret_cast<const float4*>(f.gn[q] + q3), m4 = *reinterpret_cast<const float4*>(f.gm[q] + q3);
-      float xn[4] = {x4.x + dt * (c1 * n4.x - c2 * m4.x), x4.y + dt * (c1 * n4.y - c2 * m4.y),
-                     x4.z + dt * (c1 * n4.z - c2 * m4.z), x4.w + dt * (c1 * n4.w - c2 * m4.w)};
+      float xn[4] = {ab2_upd(x4.x, dt, ab2_g(c1, c2, n4.x, m4.x)), ab2_upd(x4.y, dt, ab2_g(c1, c2, n4.y, m4.y)),
+                     ab2_upd(x4.z, dt, ab2_g(c1, c2, n4.z, m4.z)), ab2_upd(x4.w, dt, ab2_g(c1, c2, n4.w, m4.w))};
       if (imm) {
 #pragma unroll
         for (int c = 0; c < 4; c++) if (k <= kb[c]) xn[c] = 0.f;
@@ -678,6 +679,21 @@ __global__ void __launch_bounds__(128) k_ab2_ts_3d(DevGrid g, DevFields f, float
       *reinterpret_cast<float4*>(x + q3) = make_float4(xn[0], xn[1], xn[2], xn[3]);
     }
   }
+}
+// the 2-D by-products of an AB2 epilogue (barotropic forcing, transport sums) move into their model arrays when the
+// speculation is consumed: one launch, four arrays
+__global__ void k_commit_spec(int n4, const float4* __restrict__ a0, const float4* __restrict__ a1, const float4* __restrict__ a2,
+                              const float4* __restrict__ a3, float4* __restrict__ b0, float4* __restrict__ b1, float4* __restrict__ b2,
+                              float4* __restrict__ b3) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n4) return;
+  b0[q] = a0[q]; b1[q] = a1[q]; b2[q] = a2[q]; b3[q] = a3[q];
+}
+void launch_commit_spec(Handle* h) {
+  const int n4 = h->g.n2 / 4;   // PX % 4 == 0 on this path
+  k_commit_spec<<<(n4 + 255) / 256, 256, 0, h->stream>>>(n4, (const float4*)h->spec2d[0], (const float4*)h->spec2d[1], (const float4*)h->spec2d[2],
+                                                        (const float4*)h->spec2d[3], (float4*)h->f.gU, (float4*)h->f.gV, (float4*)h->us2, (float4*)h->vs2);
+  h->count_launch();
 }
 void launch_ab2_fused(Handle* h, float dt, float chi) {
   const DevGrid& g = h->g;

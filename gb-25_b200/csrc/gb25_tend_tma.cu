@@ -48,6 +48,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
   } while (!ok);
 }
+// Producer without a producer warp.  A dedicated producer warp costs a fifth of the CTA's registers (128 x 32) for seven
+// instructions per level.  Instead every consumer warp counts itself out of a stage with one shared-memory atomic when it has
+// finished a level, and the warp that arrives LAST issues the boxes of level k + NST into the stage it has just freed: the
+// refill starts the moment the stage is free, nobody polls, and the CTA is 4 warps (four CTAs per SM at 128 registers).
+// (A first version let lane 0 of warp 0 probe the empty barriers at the top of its own levels; whenever another warp was a few
+// cycles behind, the probe failed and the refill slipped by a whole level: 1.6 - 2x slower than the producer warp, measured.)
+__device__ __forceinline__ bool ring_release(int* cnt, int nwarps) {   // lane 0 of a warp, after __syncwarp(): true = last one out
+  const int old = atomicAdd_block(cnt, 1);
+  if (old != nwarps - 1) return false;
+  *cnt = 0;             // re-armed before the refill is issued: nobody counts on this stage again until its data has landed
+  return true;
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int x, int y, int z) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
@@ -400,36 +412,66 @@ __device__ __forceinline__ float2 pvert(const float (&A)[7], const float (&B)[7]
                      weno_sel_B3(B[1], B[2], B[3], B[4], B[5], B[6], BB, wt.y > 0.f, eps));
 }
 
+// Packed kernels: the Gv stage holds exactly the rows that are read — P rows j-1 .. j+7 (TY + 1), W rows j-2 .. j+8 (TY + 3) —
+// and, with the AB2 epilogue, one more box: the TX x TY tile of G- (a global load in the consumer's instruction stream is
+// needed the moment it is issued: +0.10 ms per kernel, measured; as an eighth TMA box its latency is hidden by the ring).
+#define GVP_OFF_W (GV_OFF_DX + GV_PD * (TMA_TY + 8))
+#define GVP_OFF_P (GVP_OFF_W + GV_PD * (TMA_TY + 3))
+#define GVP_STAGE (GVP_OFF_P + GV_PD * (TMA_TY + 1))
+#define MOM_GM_TILE (TMA_TX * TMA_TY)
 // ring depth: measured at 1440 x 600 x 50 (ms per launch pair): 3 stages 1.64, 4 1.63, 5 1.55, 6 1.66 (occupancy drops to 2 CTAs)
+// Producer choice per kernel, measured at 1440 x 600 x 50 (ms per launch; Gu / Gv / tracers):
+//   producer warp, 3 CTAs per SM, 5 / 6 stages   0.662 / 0.662 / 0.845
+//   last-arriver refill, 3 CTAs, 5 / 6 stages    0.703 / 0.691 / 0.804
+//   last-arriver refill, 4 CTAs, 4 / 5 stages    0.681 / 0.789 / 0.807   (the Gv stages are 15.9 KB: only 3 CTAs fit)
+// 16 instead of 12 consumer warps per SM buy nothing: the kernels are bound by the FP32 pipes, not by latency.
+#ifndef MOM_OPP
+#define MOM_OPP 0       // momentum: dedicated producer warp (5-warp CTAs)
+#endif
+#ifndef TR_OPP
+#define TR_OPP 1        // tracers: last-arriver refill (4-warp CTAs)
+#endif
 #ifndef MOM_NST
-#define MOM_NST 5
+#define MOM_NST (MOM_OPP ? 4 : 5)
 #endif
 #ifndef MOM_MINB
-#define MOM_MINB 3
+#define MOM_MINB (MOM_OPP ? 4 : 3)
 #endif
-template <int DIR>
-__global__ void __launch_bounds__(160, MOM_MINB)
-k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const float* __restrict__ own_g, float* __restrict__ G,
-             const float* __restrict__ carry) {
+#define MOM_THREADS (MOM_OPP ? 128 : 160)
+#define TR_THREADS (TR_OPP ? 128 : 160)
+// AB2 epilogue (template flag AB2): the thread that owns a column pair also applies the NEXT step's QuasiAdamsBashforth2
+// update to its own velocity component — u* = mask(u + dt (c1 Gn - c2 G-)) into the other state buffer — and accumulates,
+// level by level as it marches, the barotropic forcing sum dz mask(c1 Gn - c2 G-) and the transport sum dz u* that the
+// split-explicit solve and the corrector of the next step need (rows A8, A9, A1 of SURVEY 8a: the arithmetic and the
+// summation order of k_ab2_uv, bit for bit).  Generic cells (bathymetry in the stencil) were written by k_generic_list
+// earlier in the stream and are read back here.
+struct MomAb2 {
+  float* own_next;      // the other state buffer of this component
+  float* gsum;          // 2-D: barotropic forcing  (-> GU / GV)
+  float* usum;          // 2-D: sum dz u*           (-> the corrector's column sums)
+  float dt, c1, c2;
+};
+template <int DIR, bool AB2>
+__global__ void __launch_bounds__(MOM_THREADS, MOM_MINB)
+k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const __grid_constant__ CUtensorMap tmg, const float* __restrict__ own_g,
+             float* __restrict__ G, const float* __restrict__ carry, const MomAb2 ab) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar[MOM_NST], ebar[MOM_NST];
+  __shared__ int rcnt[MOM_NST];
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
   const int i0 = blockIdx.x * TMA_TX + 1, j0 = blockIdx.y * TMA_TY + 1;
   const int I0 = i0 + g.Hx - 1, J0 = j0 + g.Hy - 1;
   const int PX = g.PX, n2 = g.n2, Nz = g.Nz;
   const float eps = g.eps;
-  constexpr int STAGE = DIR == 0 ? GU_STAGE : GV_STAGE;
+  constexpr int OFF_GM = DIR == 0 ? GU_STAGE : GVP_STAGE;
+  constexpr int STAGE = OFF_GM + (AB2 ? MOM_GM_TILE : 0);
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < MOM_NST; s++) { mbar_init(&bar[s], 1); mbar_init(&ebar[s], 4); }
+    for (int s = 0; s < MOM_NST; s++) { mbar_init(&bar[s], 1); mbar_init(&ebar[s], 4); rcnt[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (ty >= TMA_TY) {   // ===== producer warp
-    if (tid == 128)
-      for (int k = 1; k <= Nz; k++) {
-        const int s = (k - 1) % MOM_NST;
-        if (k > MOM_NST) mbar_wait(&ebar[s], (((k - 1) / MOM_NST) - 1) & 1);
+  auto issue = [&](int k, int s) {
         float* sm = smem + s * STAGE;
         const int K = k + g.Hz - 1;
         mbar_expect_tx(&bar[s], STAGE * sizeof(float));
@@ -447,12 +489,25 @@ k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const float* __rest
           tma_load_3d(sm + GV_OFF_Z, &tm.m[2], &bar[s], I0 - 4, J0, K);
           tma_load_3d(sm + GV_OFF_DY, &tm.m[3], &bar[s], I0, J0 - 4, K);
           tma_load_3d(sm + GV_OFF_DX, &tm.m[4], &bar[s], I0, J0 - 4, K);
-          tma_load_3d(sm + GV_OFF_W, &tm.m[5], &bar[s], I0, J0 - 4, K + 1);
-          tma_load_3d(sm + GV_OFF_P, &tm.m[6], &bar[s], I0, J0 - 4, K);
+          tma_load_3d(sm + GVP_OFF_W, &tm.m[5], &bar[s], I0, J0 - 2, K + 1);
+          tma_load_3d(sm + GVP_OFF_P, &tm.m[6], &bar[s], I0, J0 - 1, K);
         }
+        if (AB2) tma_load_3d(sm + OFF_GM, &tmg, &bar[s], I0, J0, K);
+  };
+#if MOM_OPP
+  if (tid == 0)
+    for (int k = 1; k <= min(Nz, MOM_NST); k++) issue(k, k - 1);
+#else
+  if (ty >= TMA_TY) {   // ===== producer warp
+    if (tid == 128)
+      for (int k = 1; k <= Nz; k++) {
+        const int s = (k - 1) % MOM_NST;
+        if (k > MOM_NST) mbar_wait(&ebar[s], (((k - 1) / MOM_NST) - 1) & 1);
+        issue(k, s);
       }
     return;
   }
+#endif
   const int lx = 2 * tx;
   const int i = min(i0 + lx, g.Nx - 1), j = min(j0 + ty, g.Ny);
   const bool valid = (i0 + lx + 1) <= g.Nx && (j0 + ty) <= g.Ny;
@@ -479,6 +534,17 @@ k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const float* __rest
   }
   kbA = g.kb[q2]; kbB = g.kb[q2 + 1];
   const int kgen = g.kgen2[q2], kzero = g.kzero2[q2];   // pair-based (identical for both cells)
+  // AB2 epilogue: highest solid level next to each of the two velocity nodes (the node is peripheral for k <= km)
+  int kmA = 0, kmB = 0;
+  float2 gs = make_float2(0.f, 0.f), us = make_float2(0.f, 0.f);
+  if (AB2) {
+    if (DIR == 0) { kmA = max(kbA, (int)g.kb[q2 - 1]); kmB = max(kbB, kbA); }
+    else {
+      const bool ywall = y_outside(g, j) || y_outside(g, j - 1);
+      kmA = ywall ? GB25_BIG : max(kbA, (int)g.kb[q2 - PX]);
+      kmB = ywall ? GB25_BIG : max(kbB, (int)g.kb[q2 - PX + 1]);
+    }
+  }
   // ---- vertical register windows of the own velocity
   size_t q3 = q2 + (size_t)n2 * g.Hz;
   float WA[7], WB[7];
@@ -488,18 +554,18 @@ k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const float* __rest
     WA[m] = a.x; WB[m] = a.y;
   }
   float2 Wb = make_float2(0.f, 0.f);
+  int s = 0; uint32_t fph = 0;     // stage and full-barrier parity of the level being consumed
   for (int k = 1; k <= Nz; k++, q3 += n2) {
-    const int s = (k - 1) % MOM_NST;
-    mbar_wait(&bar[s], ((k - 1) / MOM_NST) & 1);
+    mbar_wait(&bar[s], fph);
     const float* sm = smem + s * STAGE;
     float2 out = make_float2(0.f, 0.f);
     bool store = false;
     if (valid) {
+      const float dz = g.dzc[k + g.Hz - 1];
       if (k <= kzero) { Wb = make_float2(0.f, 0.f); store = true; }
       else if (k > kgen) {
         store = true;
         if (k == kgen + 1 && kgen > 0) Wb = make_float2(carry[q2], carry[q2 + 1]);
-        const float dz = g.dzc[k + g.Hz - 1];
         const float2 own0 = make_float2(WA[3], WB[3]);
         const bool lA = own0.x > 0.f, lB = own0.y > 0.f;
         const int Bw = (g.immersed && k + 1 > Nz) ? 1 : 2;
@@ -550,8 +616,8 @@ k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const float* __rest
         } else {
           const float* V = sm + GV_OFF_V + (ty + 4) * GV_PV + (lx + 4); const float* U = sm + GV_OFF_U + (ty + 4) * GV_PU + (lx + 4);
           const float* Z = sm + GV_OFF_Z + ty * GV_PZ + (lx + 4); const float* DY = sm + GV_OFF_DY + (ty + 4) * GV_PD + lx;
-          const float* DX = sm + GV_OFF_DX + (ty + 4) * GV_PD + lx; const float* W = sm + GV_OFF_W + (ty + 4) * GV_PD + lx;
-          const float* P = sm + GV_OFF_P + (ty + 4) * GV_PD + lx;
+          const float* DX = sm + GV_OFF_DX + (ty + 4) * GV_PD + lx; const float* W = sm + GVP_OFF_W + (ty + 2) * GV_PD + lx;
+          const float* P = sm + GVP_OFF_P + (ty + 1) * GV_PD + lx;
           // x windows (cols i-2 .. i+3): zeta, v row j (cols i-3 .. i+3), u rows j-1 and j
           float2 vx[7], us[6], un[6], zq[6], zs[6], zr[6];
 #pragma unroll
@@ -599,13 +665,35 @@ k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const float* __rest
         out = pneg(padd(sum, rest));
       }
       if (store) *reinterpret_cast<float2*>(G + q3) = out;
+      if (AB2) {
+        const float2 gn = store ? out : *reinterpret_cast<const float2*>(G + q3);      // generic cell: left by k_generic_list
+        const float2 gmv = ldpa(sm + OFF_GM + ty * TMA_TX + lx);
+        const float gA = ab2_g(ab.c1, ab.c2, gn.x, gmv.x), gB = ab2_g(ab.c1, ab.c2, gn.y, gmv.y);
+        const bool pA = k <= kmA, pB = k <= kmB;
+        const float tA = __fmul_rn(dz, pA ? 0.f : gA), tB = __fmul_rn(dz, pB ? 0.f : gB);
+        gs.x = (k == 1) ? tA : __fadd_rn(gs.x, tA); gs.y = (k == 1) ? tB : __fadd_rn(gs.y, tB);
+        float uA = ab2_upd(WA[3], ab.dt, gA), uB = ab2_upd(WB[3], ab.dt, gB);
+        if (g.immersed) { if (pA) uA = 0.f; if (pB) uB = 0.f; }
+        *reinterpret_cast<float2*>(ab.own_next + q3) = make_float2(uA, uB);
+        const float wA = __fmul_rn(dz, uA), wB = __fmul_rn(dz, uB);
+        us.x = (k == 1) ? wA : __fadd_rn(us.x, wA); us.y = (k == 1) ? wB : __fadd_rn(us.y, wB);
+      }
       const float2 a = __ldg(reinterpret_cast<const float2*>(own_g + q3 + (size_t)4 * n2));
 #pragma unroll
       for (int m = 0; m < 6; m++) { WA[m] = WA[m + 1]; WB[m] = WB[m + 1]; }
       WA[6] = a.x; WB[6] = a.y;
     }
     __syncwarp();
+#if MOM_OPP
+    if ((tid & 31) == 0 && k + MOM_NST <= Nz && ring_release(&rcnt[s], 4)) issue(k + MOM_NST, s);
+#else
     if ((tid & 31) == 0) mbar_arrive(&ebar[s]);
+#endif
+    if (++s == MOM_NST) { s = 0; fph ^= 1u; }
+  }
+  if (AB2 && valid) {
+    *reinterpret_cast<float2*>(ab.gsum + q2) = gs;
+    *reinterpret_cast<float2*>(ab.usum + q2) = us;
   }
 }
 
@@ -625,9 +713,14 @@ k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const float* __rest
 #define TR_OFF_V (TR_OFF_U + TR_PU * TR_TY)
 #define TR_OFF_W (TR_OFF_V + TR_PV * (TR_TY + 1))
 #define TR_STAGE (TR_OFF_W + TR_PV * TR_TY)
+#define TR_GM_TILE (TR_TX * TR_TY)
 #define TR_CW 4   // consumer warps
 
 struct TmaMaps5 { CUtensorMap m[5]; };   // T, S, u, v, w
+// AB2 epilogue of the tracer kernel (template flag AB2): c' = mask(c + dt (c1 Gn - c2 G-)) into the other state buffer
+// (rows A9, A1: the arithmetic of k_ab2_ts_3d, bit for bit)
+struct TrAb2 { float* next[2]; float dt, c1, c2; };
+struct TmaMaps2 { CUtensorMap m[2]; };   // G- of T and of S
 
 __device__ __forceinline__ float weno5_selp(const float* q, bool left, float eps) {   // q[0..5], face between q[2], q[3]
   const float v0 = left ? q[0] : q[5], v1 = left ? q[1] : q[4], v2 = left ? q[2] : q[3], v3 = left ? q[3] : q[2], v4 = left ? q[4] : q[1];
@@ -636,16 +729,19 @@ __device__ __forceinline__ float weno5_selp(const float* q, bool left, float eps
 
 // ring depth (ms per launch): 4 stages 1.08, 5 1.00, 6 1.00
 #ifndef TR_NST
-#define TR_NST 6
+#define TR_NST (TR_OPP ? 4 : 6)
 #endif
 #ifndef TR_MINB
-#define TR_MINB 3
+#define TR_MINB (TR_OPP ? 4 : 3)
 #endif
-__global__ void __launch_bounds__(160, TR_MINB)
-k_tracer_tma(DevGrid g, const __grid_constant__ TmaMaps5 tm, const float* __restrict__ T0, const float* __restrict__ T1,
-             float* __restrict__ G0, float* __restrict__ G1, const float* __restrict__ carry0, const float* __restrict__ carry1) {
+template <bool AB2>
+__global__ void __launch_bounds__(TR_THREADS, TR_MINB)
+k_tracer_tma(DevGrid g, const __grid_constant__ TmaMaps5 tm, const __grid_constant__ TmaMaps2 tmg, const float* __restrict__ T0, const float* __restrict__ T1,
+             float* __restrict__ G0, float* __restrict__ G1, const float* __restrict__ carry0, const float* __restrict__ carry1,
+             const TrAb2 ab) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar[TR_NST], ebar[TR_NST];
+  __shared__ int rcnt[TR_NST];
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 16 + tx;
   const int i0 = blockIdx.x * TR_TX + 1, j0 = blockIdx.y * TR_TY + 1;
   const int I0 = i0 + g.Hx - 1, J0 = j0 + g.Hy - 1;
@@ -654,28 +750,39 @@ k_tracer_tma(DevGrid g, const __grid_constant__ TmaMaps5 tm, const float* __rest
   const float eps = g.eps;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < TR_NST; s++) { mbar_init(&bar[s], 1); mbar_init(&ebar[s], TR_CW); }
+    for (int s = 0; s < TR_NST; s++) { mbar_init(&bar[s], 1); mbar_init(&ebar[s], TR_CW); rcnt[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  constexpr int STAGE = TR_STAGE + (AB2 ? TR_GM_TILE : 0);
+  auto issue = [&](int k, int s) {
+        float* sm = smem + s * STAGE;
+        const int K = k + g.Hz - 1;
+        mbar_expect_tx(&bar[s], STAGE * sizeof(float));
+        if (AB2) tma_load_3d(sm + TR_STAGE, &tmg.m[tr], &bar[s], I0, J0, K);
+        tma_load_3d(sm + TR_OFF_T, &tm.m[tr], &bar[s], I0 - 4, J0 - 4, K);
+        tma_load_3d(sm + TR_OFF_U, &tm.m[2], &bar[s], I0, J0, K);
+        tma_load_3d(sm + TR_OFF_V, &tm.m[3], &bar[s], I0, J0, K);
+        tma_load_3d(sm + TR_OFF_W, &tm.m[4], &bar[s], I0, J0, K + 1);
+  };
+#if TR_OPP
+  if (tid == 0)
+    for (int k = 1; k <= min(Nz, TR_NST); k++) issue(k, k - 1);
+#else
   if (ty >= 8) {   // ===== producer warp
     if (tid == 128)
       for (int k = 1; k <= Nz; k++) {
         const int s = (k - 1) % TR_NST;
         if (k > TR_NST) mbar_wait(&ebar[s], (((k - 1) / TR_NST) - 1) & 1);
-        float* sm = smem + s * TR_STAGE;
-        const int K = k + g.Hz - 1;
-        mbar_expect_tx(&bar[s], TR_STAGE * sizeof(float));
-        tma_load_3d(sm + TR_OFF_T, &tm.m[tr], &bar[s], I0 - 4, J0 - 4, K);
-        tma_load_3d(sm + TR_OFF_U, &tm.m[2], &bar[s], I0, J0, K);
-        tma_load_3d(sm + TR_OFF_V, &tm.m[3], &bar[s], I0, J0, K);
-        tma_load_3d(sm + TR_OFF_W, &tm.m[4], &bar[s], I0, J0, K + 1);
+        issue(k, s);
       }
     return;
   }
+#endif
   const float* __restrict__ T = tr == 0 ? T0 : T1;
   float* __restrict__ G = tr == 0 ? G0 : G1;
   const float* __restrict__ carry = tr == 0 ? carry0 : carry1;
+  float* __restrict__ Tn = tr == 0 ? ab.next[0] : ab.next[1];
   const int lx = 2 * tx, ly = 2 * ty;                       // tile-local column / row of the patch
   const int ic = min(i0 + lx, g.Nx - 1), jc = min(j0 + ly, g.Ny - 1);   // clamped patch origin (for the hoisted loads)
   const bool vx = (i0 + lx + 1) <= g.Nx;
@@ -706,10 +813,10 @@ k_tracer_tma(DevGrid g, const __grid_constant__ TmaMaps5 tm, const float* __rest
     }
   float Fz[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
   const int oT = (ly + 4) * TR_PT + (lx + 4), oU = ly * TR_PU + lx, oV = ly * TR_PV + lx;
+  int s = 0; uint32_t fph = 0;     // stage and full-barrier parity of the level being consumed
   for (int k = 1; k <= Nz; k++, q3 += n2) {
-    const int s = (k - 1) % TR_NST;
-    mbar_wait(&bar[s], ((k - 1) / TR_NST) & 1);
-    const float* sm = smem + s * TR_STAGE;
+    mbar_wait(&bar[s], fph);
+    const float* sm = smem + s * STAGE;
     const bool fast0 = k > kg[0], fast1 = k > kg[1];
     float out[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
     if (fast0 || fast1) {
@@ -777,14 +884,27 @@ k_tracer_tma(DevGrid g, const __grid_constant__ TmaMaps5 tm, const float* __rest
     for (int r = 0; r < 2; r++) {
       const bool fast = r == 0 ? fast0 : fast1;
       if (k <= kz[r]) { Fz[r][0] = 0.f; Fz[r][1] = 0.f; out[r][0] = 0.f; out[r][1] = 0.f; }
-      if (vrow[r] && (fast || k <= kz[r])) *reinterpret_cast<float2*>(G + q3 + r * PX) = make_float2(out[r][0], out[r][1]);
+      const bool st = fast || k <= kz[r];
+      if (vrow[r] && st) *reinterpret_cast<float2*>(G + q3 + r * PX) = make_float2(out[r][0], out[r][1]);
+      if (AB2 && vrow[r]) {
+        const float2 gn = st ? make_float2(out[r][0], out[r][1]) : *reinterpret_cast<const float2*>(G + q3 + r * PX);   // generic: k_generic_list
+        const float2 gmv = ldpa(sm + TR_STAGE + (ly + r) * TR_TX + lx);
+        float c0 = ab2_upd(W[r][0][3], ab.dt, ab2_g(ab.c1, ab.c2, gn.x, gmv.x)), c1n = ab2_upd(W[r][1][3], ab.dt, ab2_g(ab.c1, ab.c2, gn.y, gmv.y));
+        if (g.immersed) { if (k <= kbc[r][0]) c0 = 0.f; if (k <= kbc[r][1]) c1n = 0.f; }
+        *reinterpret_cast<float2*>(Tn + q3 + r * PX) = make_float2(c0, c1n);
+      }
       const float2 a = __ldg(reinterpret_cast<const float2*>(T + q3 + (size_t)4 * n2 + r * PX));
 #pragma unroll
       for (int m = 0; m < 6; m++) { W[r][0][m] = W[r][0][m + 1]; W[r][1][m] = W[r][1][m + 1]; }
       W[r][0][6] = a.x; W[r][1][6] = a.y;
     }
     __syncwarp();
+#if TR_OPP
+    if ((tid & 31) == 0 && k + TR_NST <= Nz && ring_release(&rcnt[s], TR_CW)) issue(k + TR_NST, s);
+#else
     if ((tid & 31) == 0) mbar_arrive(&ebar[s]);
+#endif
+    if (++s == TR_NST) { s = 0; fph ^= 1u; }
   }
 }
 
@@ -813,7 +933,8 @@ static bool make_map(const DevGrid& g, const float* base, int bx, int by, CUtens
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-struct TmaState { bool ready = false, ok = false; TmaMaps7 gu, gv; TmaMaps5 tr; };
+// [parity of the state buffers]; gm: G- tiles of u, v, T, S for the AB2 epilogues ([parity of the Gn / G- pointer swap])
+struct TmaState { bool ready = false, ok = false; TmaMaps7 gu[2], gv[2]; TmaMaps5 tr[2]; CUtensorMap gm[2][4]; const float* gm_base[2][4]; };
 static TmaState* tma_state(Handle* h) {
   if (!h->tma) h->tma = new TmaState();
   TmaState* t = (TmaState*)h->tma;
@@ -823,29 +944,41 @@ static TmaState* tma_state(Handle* h) {
   if (g.PX % 4) return t;   // TMA needs 16-byte row pitch
   const int TX = TMA_TX, TY = TMA_TY;
   bool ok = true;
-  ok &= make_map(g, h->f.u, TX + 8, TY + 8, &t->gu.m[0]);
-  ok &= make_map(g, h->f.v, TX + 4, TY + 8, &t->gu.m[1]);
-  ok &= make_map(g, h->zeta, TX, TY + 8, &t->gu.m[2]);
-  ok &= make_map(g, h->dxU, TX + 8, TY, &t->gu.m[3]);
-  ok &= make_map(g, h->dyV, TX + 8, TY, &t->gu.m[4]);
-  ok &= make_map(g, h->f.w, TX + 8, TY, &t->gu.m[5]);
-  ok &= make_map(g, h->f.p, TX + 4, TY, &t->gu.m[6]);
-  ok &= make_map(g, h->f.v, TX + 8, TY + 8, &t->gv.m[0]);
-  ok &= make_map(g, h->f.u, TX + 8, TY + 8, &t->gv.m[1]);
-  ok &= make_map(g, h->zeta, TX + 8, TY, &t->gv.m[2]);
-  ok &= make_map(g, h->dyV, TX, TY + 8, &t->gv.m[3]);
-  ok &= make_map(g, h->dxU, TX, TY + 8, &t->gv.m[4]);
-  ok &= make_map(g, h->f.w, TX, TY + 8, &t->gv.m[5]);
-  ok &= make_map(g, h->f.p, TX, TY + 8, &t->gv.m[6]);
-  ok &= make_map(g, h->f.T, TR_TX + 8, TR_TY + 8, &t->tr.m[0]);
-  ok &= make_map(g, h->f.S, TR_TX + 8, TR_TY + 8, &t->tr.m[1]);
-  ok &= make_map(g, h->f.u, TR_TX + 4, TR_TY, &t->tr.m[2]);
-  ok &= make_map(g, h->f.v, TR_TX, TR_TY + 1, &t->tr.m[3]);
-  ok &= make_map(g, h->f.w, TR_TX, TR_TY, &t->tr.m[4]);
+  for (int par = 0; par < 2; par++) {
+    const float *u = h->state_buf[par][0], *v = h->state_buf[par][1], *T = h->state_buf[par][2], *S = h->state_buf[par][3];
+    ok &= make_map(g, u, TX + 8, TY + 8, &t->gu[par].m[0]);
+    ok &= make_map(g, v, TX + 4, TY + 8, &t->gu[par].m[1]);
+    ok &= make_map(g, h->zeta, TX, TY + 8, &t->gu[par].m[2]);
+    ok &= make_map(g, h->dxU, TX + 8, TY, &t->gu[par].m[3]);
+    ok &= make_map(g, h->dyV, TX + 8, TY, &t->gu[par].m[4]);
+    ok &= make_map(g, h->f.w, TX + 8, TY, &t->gu[par].m[5]);
+    ok &= make_map(g, h->f.p, TX + 4, TY, &t->gu[par].m[6]);
+    ok &= make_map(g, v, TX + 8, TY + 8, &t->gv[par].m[0]);
+    ok &= make_map(g, u, TX + 8, TY + 8, &t->gv[par].m[1]);
+    ok &= make_map(g, h->zeta, TX + 8, TY, &t->gv[par].m[2]);
+    ok &= make_map(g, h->dyV, TX, TY + 8, &t->gv[par].m[3]);
+    ok &= make_map(g, h->dxU, TX, TY + 8, &t->gv[par].m[4]);
+    ok &= make_map(g, h->f.w, TX, TY + 3, &t->gv[par].m[5]);
+    ok &= make_map(g, h->f.p, TX, TY + 1, &t->gv[par].m[6]);
+    ok &= make_map(g, T, TR_TX + 8, TR_TY + 8, &t->tr[par].m[0]);
+    ok &= make_map(g, S, TR_TX + 8, TR_TY + 8, &t->tr[par].m[1]);
+    ok &= make_map(g, u, TR_TX + 4, TR_TY, &t->tr[par].m[2]);
+    ok &= make_map(g, v, TR_TX, TR_TY + 1, &t->tr[par].m[3]);
+    ok &= make_map(g, h->f.w, TR_TX, TR_TY, &t->tr[par].m[4]);
+  }
+  // the Gn / G- arrays swap roles every step: one G- map per array, looked up by base pointer at launch
+  for (int q = 0; q < 4; q++) {
+    t->gm_base[0][q] = h->f.gm[q]; t->gm_base[1][q] = h->f.gn[q];
+    for (int r = 0; r < 2; r++) ok &= make_map(g, t->gm_base[r][q], q < 2 ? TX : TR_TX, q < 2 ? TY : TR_TY, &t->gm[r][q]);
+  }
   if (ok) {
-    ok &= cudaFuncSetAttribute(k_tracer_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_NST * TR_STAGE * (int)sizeof(float)) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(k_mom_tma_p2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, MOM_NST * GU_STAGE * (int)sizeof(float)) == cudaSuccess;
-    ok &= cudaFuncSetAttribute(k_mom_tma_p2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MOM_NST * GV_STAGE * (int)sizeof(float)) == cudaSuccess;
+    const int f4 = (int)sizeof(float);
+    ok &= cudaFuncSetAttribute(k_tracer_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_NST * TR_STAGE * f4) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(k_tracer_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_NST * (TR_STAGE + TR_GM_TILE) * f4) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(k_mom_tma_p2<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MOM_NST * GU_STAGE * f4) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(k_mom_tma_p2<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MOM_NST * (GU_STAGE + MOM_GM_TILE) * f4) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(k_mom_tma_p2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MOM_NST * GVP_STAGE * f4) == cudaSuccess;
+    ok &= cudaFuncSetAttribute(k_mom_tma_p2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MOM_NST * (GVP_STAGE + MOM_GM_TILE) * f4) == cudaSuccess;
     ok &= cudaFuncSetAttribute(k_gu_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GU_STAGE * (int)sizeof(float)) == cudaSuccess;
     ok &= cudaFuncSetAttribute(k_gv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_NST * GV_STAGE * (int)sizeof(float)) == cudaSuccess;
   }
@@ -855,33 +988,55 @@ static TmaState* tma_state(Handle* h) {
 bool tma_available(Handle* h) { return tma_state(h)->ok; }
 void tma_free(Handle* h) { delete (TmaState*)h->tma; h->tma = nullptr; }
 
-void launch_momentum_tendency_tma(Handle* h) {
+static const CUtensorMap& gm_map(TmaState* t, const float* base, int q) { return t->gm[t->gm_base[0][q] == base ? 0 : 1][q]; }
+void launch_momentum_tendency_tma(Handle* h, const Ab2Spec* spec) {
   TmaState* t = tma_state(h);
   const DevGrid& g = h->g;
+  const int par = h->parity;
   if (h->use_packed) {
-    dim3 b(16, TMA_TY + 2), gr((g.Nx + TMA_TX - 1) / TMA_TX, (g.Ny + TMA_TY - 1) / TMA_TY);
+    dim3 b(16, MOM_THREADS / 16), gr((g.Nx + TMA_TX - 1) / TMA_TX, (g.Ny + TMA_TY - 1) / TMA_TY);
+    const int gmt = spec ? MOM_GM_TILE : 0;
+    const size_t smu = MOM_NST * (GU_STAGE + gmt) * sizeof(float), smv = MOM_NST * (GVP_STAGE + gmt) * sizeof(float);
+    MomAb2 au = {}, av = {};
+    if (spec) {
+      au = MomAb2{h->state_buf[1 - par][0], h->spec2d[0], h->spec2d[2], spec->dt, spec->c1, spec->c2};
+      av = MomAb2{h->state_buf[1 - par][1], h->spec2d[1], h->spec2d[3], spec->dt, spec->c1, spec->c2};
+    }
     { StageScope ts(h, "kernel:k_gu_tma");
-      k_mom_tma_p2<0><<<gr, b, MOM_NST * GU_STAGE * sizeof(float), h->stream>>>(g, t->gu, h->f.u, h->f.gn[0], h->carry[0]); }
+      if (spec) k_mom_tma_p2<0, true><<<gr, b, smu, h->stream>>>(g, t->gu[par], gm_map(t, h->f.gm[0], 0), h->f.u, h->f.gn[0], h->carry[0], au);
+      else k_mom_tma_p2<0, false><<<gr, b, smu, h->stream>>>(g, t->gu[par], gm_map(t, h->f.gm[0], 0), h->f.u, h->f.gn[0], h->carry[0], au); }
     h->count_launch();
     { StageScope ts(h, "kernel:k_gv_tma");
-      k_mom_tma_p2<1><<<gr, b, MOM_NST * GV_STAGE * sizeof(float), h->stream>>>(g, t->gv, h->f.v, h->f.gn[1], h->carry[1]); }
+      if (spec) k_mom_tma_p2<1, true><<<gr, b, smv, h->stream>>>(g, t->gv[par], gm_map(t, h->f.gm[1], 1), h->f.v, h->f.gn[1], h->carry[1], av);
+      else k_mom_tma_p2<1, false><<<gr, b, smv, h->stream>>>(g, t->gv[par], gm_map(t, h->f.gm[1], 1), h->f.v, h->f.gn[1], h->carry[1], av); }
     h->count_launch();
     return;
   }
+  // scalar TMA kernels (GB25_PACKED=0): their Gv stage keeps full-height W and P boxes
+  TmaMaps7 gvs = t->gv[par];
+  make_map(g, h->f.w, TMA_TX, TMA_TY + 8, &gvs.m[5]);
+  make_map(g, h->f.p, TMA_TX, TMA_TY + 8, &gvs.m[6]);
   dim3 b(TMA_TX, TMA_TY + 1), gr((g.Nx + TMA_TX - 1) / TMA_TX, (g.Ny + TMA_TY - 1) / TMA_TY);
   { StageScope ts(h, "kernel:k_gu_tma");
-  k_gu_tma<<<gr, b, TMA_NST * GU_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gu, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[0], h->carry[0]); }
+  k_gu_tma<<<gr, b, TMA_NST * GU_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gu[par], h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[0], h->carry[0]); }
   h->count_launch();
   { StageScope ts(h, "kernel:k_gv_tma");
-  k_gv_tma<<<gr, b, TMA_NST * GV_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, t->gv, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[1], h->carry[1]); }
+  k_gv_tma<<<gr, b, TMA_NST * GV_STAGE * sizeof(float), h->stream>>>(g, h->g_dev, gvs, h->f.u, h->f.v, h->f.w, h->f.p, h->f.gn[1], h->carry[1]); }
   h->count_launch();
 }
 
-void launch_tracer_tendency_tma(Handle* h) {
+void launch_tracer_tendency_tma(Handle* h, const Ab2Spec* spec) {
   TmaState* t = tma_state(h);
   const DevGrid& g = h->g;
-  dim3 b(16, 10), gr((g.Nx + TR_TX - 1) / TR_TX, (g.Ny + TR_TY - 1) / TR_TY, 2);
+  const int par = h->parity;
+  dim3 b(16, TR_THREADS / 16), gr((g.Nx + TR_TX - 1) / TR_TX, (g.Ny + TR_TY - 1) / TR_TY, 2);
+  const size_t sm = TR_NST * (TR_STAGE + (spec ? TR_GM_TILE : 0)) * sizeof(float);
+  TrAb2 ab = {};
+  TmaMaps2 tmg;
+  tmg.m[0] = gm_map(t, h->f.gm[2], 2); tmg.m[1] = gm_map(t, h->f.gm[3], 3);
+  if (spec) ab = TrAb2{{h->state_buf[1 - par][2], h->state_buf[1 - par][3]}, spec->dt, spec->c1, spec->c2};
   StageScope ts(h, "kernel:k_tracer_tma");
-  k_tracer_tma<<<gr, b, TR_NST * TR_STAGE * sizeof(float), h->stream>>>(g, t->tr, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3], h->carry[2], h->carry[3]);
+  if (spec) k_tracer_tma<true><<<gr, b, sm, h->stream>>>(g, t->tr[par], tmg, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3], h->carry[2], h->carry[3], ab);
+  else k_tracer_tma<false><<<gr, b, sm, h->stream>>>(g, t->tr[par], tmg, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3], h->carry[2], h->carry[3], ab);
   h->count_launch();
 }

@@ -13,7 +13,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgb25cuda.so")
+# GB25_LIB selects another in-tree build of the same library (kernel experiments: gb25_b200.build --suffix); it is never
+# a different implementation, and a missing file still fails loudly.
+LIB_PATH = os.environ.get("GB25_LIB") or os.path.join(_HERE, "csrc", "libgb25cuda.so")
 
 GB25_OK, GB25_ERR_INVALID, GB25_ERR_NO_DEVICE, GB25_ERR_CUDA, GB25_ERR_ALLOC, GB25_ERR_COMM = 0, -1, -2, -3, -4, -5
 
