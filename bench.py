@@ -42,10 +42,14 @@ WORKLOADS = {
 ALGORITHMIC_BYTES_PER_CELL_STEP = 104     # 26 Float32 words of compulsory 3-D traffic
 # algorithmic bytes per cell of one launch of each tendency kernel (DESIGN.md "kernels")
 # ("kernel:<name>" entries are single-launch CUDA-event timers of libgb25cuda)
+# With the AB2 epilogue (the path gb25_loop takes) a tendency kernel also reads its G- and writes the updated state.
 KERNEL_BYTES_PER_CELL = {"kernel:k_tracer_tendency_v2": (5 + 2) * 4,   # one launch, both tracers: read u,v,w,T,S, write GT,GS
                          "kernel:k_tracer_tma": (5 + 2) * 4,
+                         "kernel:k_tracer_tma+ab2": (7 + 4) * 4,        # + read G-T, G-S, write T', S'
                          "kernel:k_gu_tma": (4 + 1) * 4,                # read u,v,w,p, write Gu
                          "kernel:k_gv_tma": (4 + 1) * 4,
+                         "kernel:k_gu_tma+ab2": (5 + 2) * 4,            # + read G-u, write u*
+                         "kernel:k_gv_tma+ab2": (5 + 2) * 4,
                          "kernel:k_ab2_fused": 16 * 4,                  # read 4 fields + 8 G, write 4 fields
                          "momentum_tendencies": 2 * (4 + 1) * 4, "tracer_tendencies": (5 + 2) * 4}
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) comes from profiles/ncu_traffic.json, written by
@@ -401,7 +405,12 @@ def main():
     hbm, peak_src = measured_peaks()
     # dominant kernel = the stage with the largest share of the step
     kernels = {k: v for k, v in stages.items() if k.startswith("kernel:")}
-    stages = {k: v for k, v in stages.items() if not k.startswith("kernel:")}
+    exch = {k: v for k, v in stages.items() if k.startswith("exchange:")}
+    stages = {k: v for k, v in stages.items() if not k.startswith(("kernel:", "exchange:"))}
+    if "ab2_step_fields" in stages and "kernel:k_ab2_fused" not in kernels:      # the AB2 stage was a pointer swap: epilogue path
+        for k in ("kernel:k_tracer_tma", "kernel:k_gu_tma", "kernel:k_gv_tma"):
+            if k in kernels:
+                kernels[k + "+ab2"] = kernels.pop(k)
     tot_ms = sum(ms for ms, _ in stages.values()) or 1.0
     pool = kernels if any(k in KERNEL_BYTES_PER_CELL for k in kernels) else stages
     dom = max((k for k in pool if k in KERNEL_BYTES_PER_CELL), key=lambda k: pool[k][0], default=None)
@@ -413,7 +422,8 @@ def main():
         achieved = KERNEL_BYTES_PER_CELL[dom] * cells_per_rank / per_call_s / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s",
                     "frac": achieved / hbm,
-                    "traffic": (traffic_tab.get(dom[7:], {}).get("dram_bytes") if args.workload == "tripolar_quarter_degree" else None),
+                    "traffic": (traffic_tab.get(dom[7:].replace("+ab2", ""), {}).get("dram_bytes")
+                                if args.workload == "tripolar_quarter_degree" else None),
                     "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": KERNEL_BYTES_PER_CELL[dom] * cells_per_rank, "peak_source": peak_src,
                     "avg_launch_ms": per_call_s * 1e3, "share_of_step": ms / tot_ms,
@@ -423,7 +433,8 @@ def main():
                                    "achieved": ALGORITHMIC_BYTES_PER_CELL_STEP * value / world / 1e9,
                                    "frac": ALGORITHMIC_BYTES_PER_CELL_STEP * value / world / 1e9 / hbm},
                     "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
-                    "kernel_ms_per_launch": {k[7:]: v[0] / max(v[1], 1) for k, v in kernels.items()}}
+                    "kernel_ms_per_launch": {k[7:]: v[0] / max(v[1], 1) for k, v in kernels.items()},
+                    "exchange_ms_per_step": {k[9:]: v[0] / args.steps for k, v in exch.items()}}
     line = {"metric": "cell_steps_per_s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak",

@@ -54,6 +54,33 @@ __global__ void k_push_cols(DevGrid g, PushBatch pb, int scol, int dcol, int nco
   const size_t po = (three_d ? (size_t)g.n2 * blockIdx.y : 0) + (size_t)g.PX * J;
   pf.dst[po + dcol + cI] = pf.src[po + scol + cI];
 }
+// West / east strips travel PACKED.  Written straight into the neighbour's halo columns they are 32-byte pieces at a pitch
+// of PX floats, and NVLink moves those at ~50 GB/s (measured: 0.22 ms per step for 11 MB at 1440 x 600 x 50 tiles, six
+// times the cost of the row strips).  Here a warp gathers four rows x Hx columns and stores them as one contiguous 128-byte
+// line into the neighbour's column inbox; after the handshake the receiver scatters its inbox into its own halo columns
+// (a local copy).  The inbox has two halves, used alternately by sequence parity: a neighbour that runs ahead may already
+// push the strips of the NEXT fill while this tile has not unpacked the current one.
+__global__ void k_push_cols_packed(DevGrid g, PushBatch pb, int scol, int three_d, float* __restrict__ box) {
+  const int c = threadIdx.x;                                  // 0 .. Hx-1
+  const int J = blockIdx.x * blockDim.y + threadIdx.y;        // storage row
+  if (c >= g.Hx || J >= g.PY) return;
+  const PushField pf = pb.f[blockIdx.z];
+  if (pf.flat) { if (blockIdx.y > 0) return; three_d = 0; }
+  const size_t po = (three_d ? (size_t)g.n2 * blockIdx.y : 0) + (size_t)g.PX * J;
+  box[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * g.PY + J) * g.Hx + c] = pf.src[po + scol + c];
+}
+// blockIdx.z = 2 * field slot + direction (0: from the west tile -> columns [0, Hx), 1: from the east tile -> [Nx+Hx, PX))
+__global__ void k_unpack_cols(DevGrid g, PushBatch pb, int three_d, const float* __restrict__ box_w, const float* __restrict__ box_e) {
+  const int c = threadIdx.x;
+  const int J = blockIdx.x * blockDim.y + threadIdx.y;
+  if (c >= g.Hx || J >= g.PY) return;
+  const int q = blockIdx.z >> 1, dir = blockIdx.z & 1;
+  const PushField pf = pb.f[q];
+  if (pf.flat) { if (blockIdx.y > 0) return; three_d = 0; }
+  const size_t po = (three_d ? (size_t)g.n2 * blockIdx.y : 0) + (size_t)g.PX * J;
+  const float* box = dir ? box_e : box_w;
+  pf.dst[po + (dir ? g.Nx + g.Hx : 0) + c] = box[(((size_t)q * gridDim.y + blockIdx.y) * g.PY + J) * g.Hx + c];
+}
 // tripolar fold: my top rows -> the partner's north halo rows, x-mirrored, sign-flipped for vectors.
 // `second` selects the Face-x column whose partner lives one tile further (see the header comment of
 // fold_index_maps in grids.py / SURVEY A.5); quirk_pos: that element keeps |sign| (global wrap past Nx).
@@ -97,13 +124,13 @@ __global__ void k_wait(volatile int* flags, int mask, int val) {
 void exchange_table(Handle* h, float* tab[EX_NF]) {
   const DevFields& f = h->f;
   float* t[EX_NF] = {h->state_buf[0][0], h->state_buf[0][1], h->state_buf[0][2], h->state_buf[0][3], f.eta, f.bu, f.bv, f.gU, f.gV,
-                     h->state_buf[1][0], h->state_buf[1][1], h->state_buf[1][2], h->state_buf[1][3]};
+                     h->state_buf[1][0], h->state_buf[1][1], h->state_buf[1][2], h->state_buf[1][3], h->ex.xbox};
   for (int q = 0; q < EX_NF; q++) tab[q] = t[q];
 }
 static int ex_field_id(Handle* h, const float* a) {
   float* tab[EX_NF];
   exchange_table(h, tab);
-  for (int q = 0; q < EX_NF; q++) if (tab[q] == a) return q;
+  for (int q = 0; q < EX_NF; q++) if (q != EX_XBOX && tab[q] == a) return q;
   return -1;
 }
 static const ExSlot kOpposite[EX_NSLOT] = {SLOT_E, SLOT_W, SLOT_N, SLOT_S, SLOT_FOLD, SLOT_FOLD2};
@@ -180,11 +207,13 @@ void launch_fill_halo_dist(Handle* h, const HaloSpec* specs, int n, bool three_d
   const bool fold = c.topo_y == GB25_TOPO_FOLD && top;
   const int np = three_d ? g.PZ : 1;
   // ---- wall conditions of the boundary tiles, then z halos of the interior columns (local)
+  { StageScope ts(h, "exchange:local_fills");
   launch_halo_south_north(h, specs, n, three_d, bottom ? 1 : 0, (top && c.topo_y == GB25_TOPO_BOUNDED) ? 1 : ((fold && c.Rx == 1) ? 2 : 0));
-  if (three_d) launch_halo_bottom_top(h, specs, n);
+  if (three_d) launch_halo_bottom_top(h, specs, n); }
   // ---- phase Y: strips to the north / south tiles (all planes), fold rows to the mirrored partner
   int mask_y = 0;
   dim3 b(128);
+  StageScope* tsy = new StageScope(h, "exchange:push_y");
   if (!top) {
     PushBatch pb = make_push(h, specs, n, SLOT_N);
     dim3 gr((g.Nx + 127) / 128, g.Hy * np, pb.n);
@@ -209,20 +238,38 @@ void launch_fill_halo_dist(Handle* h, const HaloSpec* specs, int n, bool three_d
     if (p2.n) { k_push_fold<<<g2, b, 0, h->stream>>>(g, p2, three_d, g.Hy, 1, c.rx == 0 ? 1 : 0); h->count_launch(); }
     mask_y |= (1 << SLOT_FOLD) | (1 << SLOT_FOLD2);
   }
-  if (mask_y) { X.seq++; signal_slots(h, mask_y); wait_slots(h, mask_y); }
+  delete tsy;
+  if (mask_y) { StageScope ts(h, "exchange:handshake_y"); X.seq++; signal_slots(h, mask_y); wait_slots(h, mask_y); }
   // ---- phase X: west / east strips over the full parent extent (carries the y and z halos into the corners)
   if (c.Rx == 1) { launch_halo_periodic_x(h, specs, n, three_d); return; }
   {
     dim3 bc(g.Hx, 32), gc((g.PY + 31) / 32, np, 0);
-    PushBatch pe = make_push(h, specs, n, SLOT_E);   // my last Hx interior columns -> the east tile's west halo
-    gc.z = pe.n;
-    if (pe.n) { k_push_cols<<<gc, bc, 0, h->stream>>>(g, pe, g.Nx, 0, g.Hx, three_d, 0, g.PY); h->count_launch(); }
-    PushBatch pw = make_push(h, specs, n, SLOT_W);   // my first Hx interior columns -> the west tile's east halo
-    gc.z = pw.n;
-    if (pw.n) { k_push_cols<<<gc, bc, 0, h->stream>>>(g, pw, g.Hx, g.Nx + g.Hx, g.Hx, three_d, 0, g.PY); h->count_launch(); }
     X.seq++;
-    const int mx = (1 << SLOT_W) | (1 << SLOT_E);
-    signal_slots(h, mx); wait_slots(h, mx);
+    X.xseq++;     // (the parity of the column phases, not of all phases: a fill with a row phase advances seq twice)
+    float* const mybox = X.xbox + (size_t)(X.xseq & 1) * 2 * X.xbox_stride;
+    {
+      StageScope ts(h, "exchange:push_x");
+      const size_t off = (size_t)(X.xseq & 1) * 2 * X.xbox_stride;
+      PushBatch pe = make_push(h, specs, n, SLOT_E);   // my last Hx interior columns -> the east tile's inbox "from the west"
+      gc.z = pe.n;
+      if (pe.n) { k_push_cols_packed<<<gc, bc, 0, h->stream>>>(g, pe, g.Nx, three_d, X.to[SLOT_E].fld[EX_XBOX] + off); h->count_launch(); }
+      PushBatch pw = make_push(h, specs, n, SLOT_W);   // my first Hx interior columns -> the west tile's inbox "from the east"
+      gc.z = pw.n;
+      if (pw.n) { k_push_cols_packed<<<gc, bc, 0, h->stream>>>(g, pw, g.Hx, three_d, X.to[SLOT_W].fld[EX_XBOX] + off + X.xbox_stride); h->count_launch(); }
+    }
+    {
+      StageScope ts(h, "exchange:handshake_x");
+      const int mx = (1 << SLOT_W) | (1 << SLOT_E);
+      signal_slots(h, mx); wait_slots(h, mx);
+    }
+    {
+      StageScope ts(h, "exchange:unpack_x");
+      PushBatch pu; pu.n = 0;
+      for (int q = 0; q < n; q++)
+        if (ex_field_id(h, specs[q].a) >= 0) pu.f[pu.n++] = PushField{nullptr, specs[q].a, specs[q].lx, specs[q].ly, specs[q].lz, specs[q].sign, specs[q].flat};
+      gc.z = 2 * pu.n;
+      if (pu.n) { k_unpack_cols<<<gc, bc, 0, h->stream>>>(g, pu, three_d, mybox, mybox + X.xbox_stride); h->count_launch(); }
+    }
   }
 }
 
@@ -264,6 +311,11 @@ extern "C" int gb25_exchange_export(gb25_handle* h, void* blob) {
     // a dedicated 2 MiB allocation so that the IPC handle maps exactly this buffer
     if (cudaMalloc(&X.flags, 2 << 20) != cudaSuccess) { h->err = "gb25_exchange_export: cudaMalloc flags"; return GB25_ERR_ALLOC; }
     cudaMemset(X.flags, 0, 2 << 20);
+  }
+  if (!X.xbox) {
+    X.xbox_stride = (size_t)9 * h->g.PZ * h->g.PY * h->g.Hx;
+    if (cudaMalloc(&X.xbox, 4 * X.xbox_stride * sizeof(float)) != cudaSuccess) { h->err = "gb25_exchange_export: cudaMalloc column inbox"; return GB25_ERR_ALLOC; }
+    cudaMemset(X.xbox, 0, 4 * X.xbox_stride * sizeof(float));
   }
   float* tab[EX_NF];
   exchange_table(h, tab);
@@ -337,7 +389,7 @@ extern "C" int gb25_exchange_connect(gb25_handle* h, const void* blobs, int nran
   // session (a stale number would satisfy a wait).  The caller synchronises all ranks before reconnecting and puts a
   // barrier after it (distributed.connect), so no neighbour writes into this buffer while it is cleared.
   if (cudaMemset(X.flags, 0, 2 << 20) != cudaSuccess) { h->err = "gb25_exchange_connect: cudaMemset flags"; return GB25_ERR_CUDA; }
-  X.seq = 0;
+  X.seq = 0; X.xseq = 0;
   X.on = true;
   baro_plan_free(h);   // the persistent substep kernel restarts its sequence numbers on the (zeroed) shared flag buffer
   return GB25_OK;
@@ -353,5 +405,6 @@ void exchange_close(Handle* h) {
   for (void* p : h->ex.opened) cudaIpcCloseMemHandle(p);
   h->ex.opened.clear();
   if (h->ex.flags) { cudaFree(h->ex.flags); h->ex.flags = nullptr; }
+  if (h->ex.xbox) { cudaFree(h->ex.xbox); h->ex.xbox = nullptr; }
   h->ex.on = false;
 }

@@ -13,16 +13,19 @@ struct HaloSpec { float* a; int lx, ly, lz; float sign; int flat; };   // flat =
 // ---- multi-GPU halo exchange over peer-mapped (CUDA IPC) memory, one process per GPU (gb25_exchange.cu)
 // exported allocations: both halves of the double-buffered 3-D state (all tiles flip in lockstep, so a tile's current
 // buffer always faces its neighbours' current buffers) and the 2-D fields
-enum ExField { EX_U = 0, EX_V, EX_T, EX_S, EX_ETA, EX_BU, EX_BV, EX_GU, EX_GV, EX_U2, EX_V2, EX_T2, EX_S2, EX_NF };
+// EX_XBOX: the column inbox (west / east strips arrive packed, see k_push_cols_packed)
+enum ExField { EX_U = 0, EX_V, EX_T, EX_S, EX_ETA, EX_BU, EX_BV, EX_GU, EX_GV, EX_U2, EX_V2, EX_T2, EX_S2, EX_XBOX, EX_NF };
 enum ExSlot { SLOT_W = 0, SLOT_E, SLOT_S, SLOT_N, SLOT_FOLD, SLOT_FOLD2, EX_NSLOT };
 struct ExPeer { float* fld[EX_NF]; int* flags; int rank; };
 struct Exchange {
   bool on = false;
   int nranks = 1, rank = 0;
   int* flags = nullptr;          // local inbox: EX_NSLOT sequence numbers written by the neighbours + 1 error word
+  float* xbox = nullptr;         // local column inbox: [seq parity][from west, from east][field slot][plane][row][Hx]
+  size_t xbox_stride = 0;        // floats per (parity, direction) box
   ExPeer to[EX_NSLOT];           // the tile lying in that direction (destination of my pushes); rank < 0: none
   int from_mask_y = 0, from_mask_x = 0, from_mask_fold = 0;   // slots I receive on in each phase
-  int seq = 0;
+  int seq = 0, xseq = 0;
   std::vector<void*> opened;     // pointers returned by cudaIpcOpenMemHandle
 };
 
