@@ -326,6 +326,8 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     h->use_tma = !(t && t[0] == '0');
     const char* sp = getenv("GB25_SPECULATE");
     h->use_spec = !(sp && sp[0] == '0');
+    const char* zf = getenv("GB25_ZHALO_FOLD");
+    h->use_zfold = !(zf && zf[0] == '0');
     const char* pk = getenv("GB25_PACKED");
     h->use_packed = !(pk && pk[0] == '0');
     const char* tt = getenv("GB25_TMA_TRACER");
@@ -420,10 +422,11 @@ static void fill_prognostic(Handle* h) {
 // those halos in between (the substep kernels take GU,GV at interior points and start from the halos of the previous
 // step's fill), and the later fill overwrites every halo cell of the earlier ones, so the state after the step is the same —
 // with one exchange sequence between tiles instead of four.
-static void fill_prognostic_fused(Handle* h) {
+static void fill_prognostic_fused(Handle* h, bool zdone_uv, bool zdone_ts) {
   StageScope t(h, "fill_halo_regions");
   DevFields& f = h->f;
-  HaloSpec s[9] = {{f.u, 1, 0, 0, -1.f, 0}, {f.v, 0, 1, 0, -1.f, 0}, {f.T, 0, 0, 0, 1.f, 0}, {f.S, 0, 0, 0, 1.f, 0},
+  const int zu = zdone_uv ? 1 : 0, zv = zdone_uv ? 2 : 0, zt = zdone_ts ? 1 : 0;
+  HaloSpec s[9] = {{f.u, 1, 0, 0, -1.f, 0, zu}, {f.v, 0, 1, 0, -1.f, 0, zv}, {f.T, 0, 0, 0, 1.f, 0, zt}, {f.S, 0, 0, 0, 1.f, 0, zt},
                    {f.eta, 0, 0, 1, 1.f, 1}, {f.bu, 1, 0, 0, -1.f, 1}, {f.bv, 0, 1, 0, -1.f, 1},
                    {f.gU, 1, 0, 0, -1.f, 1}, {f.gV, 0, 1, 0, -1.f, 1}};
   launch_fill_halo(h, s, 9, true);
@@ -476,7 +479,9 @@ static void swap_state_buffers(Handle* h) {
 // fused step path: identical results, fewer passes over the 3-D state (see gb25_kernels.cu "Fused step path")
 static void one_time_step_fused(Handle* h, float dt, float chi) {
   DevFields& f = h->f;
+  bool zdone_ts = false;
   if (h->spec.valid && h->spec.dt == dt && h->spec.chi == chi) {
+    zdone_ts = h->spec.zhalo;
     // the tendency kernels of the previous step already wrote u*, v*, T', S' (masked) into the other state buffers and
     // GU, GV, sum dz u*, sum dz v* into their 2-D arrays: the AB2 stage is a pointer swap
     StageScope t(h, "ab2_step_fields");
@@ -489,19 +494,20 @@ static void one_time_step_fused(Handle* h, float dt, float chi) {
   if (h->cfg.closure == 2) { StageScope t(h, "vertical_diffusion"); launch_implicit_columns(h, dt, true); }
   { StageScope t(h, "split_explicit_free_surface"); launch_barotropic(h, dt); }
   h->time += (double)dt; h->iteration += 1; h->last_dt = dt;
-  { StageScope t(h, "correct_velocities_and_cache"); launch_correct_fused(h); }
+  bool zdone_uv;
+  { StageScope t(h, "correct_velocities_and_cache"); zdone_uv = launch_correct_fused(h); }
   // G- <- Gn: swap the buffers; the tendency kernels below overwrite the whole interior of the new Gn,
   // and the halos of both are identically zero
   for (int q = 0; q < 4; q++) {
     std::swap(f.gn[q], f.gm[q]);
     std::swap(h->field_ptr[GB25_GN_U + q], h->field_ptr[GB25_GM_U + q]);
   }
-  fill_prognostic_fused(h);
+  fill_prognostic_fused(h, zdone_uv, zdone_ts && h->cfg.closure != 2);   // (the implicit solve rewrites T, S after the epilogue)
   stage_aux(h);
   if (spec_possible(h)) {
-    const Ab2Spec sp = {dt, 1.5f + h->cfg.chi, 0.5f + h->cfg.chi};
+    const Ab2Spec sp = {dt, 1.5f + h->cfg.chi, 0.5f + h->cfg.chi, (h->use_zfold && h->g.Nz >= h->g.Hz) ? 1 : 0};
     stage_tend(h, &sp);
-    h->spec.valid = true; h->spec.dt = dt; h->spec.chi = h->cfg.chi;
+    h->spec.valid = true; h->spec.dt = dt; h->spec.chi = h->cfg.chi; h->spec.zhalo = sp.zhalo != 0;
   } else {
     stage_tend(h);
   }

@@ -8,7 +8,9 @@
 #include "../../include/gb25cuda.h"
 #include "gb25_device.cuh"
 
-struct HaloSpec { float* a; int lx, ly, lz; float sign; int flat; };   // flat = 1: a 2-D field riding in a batch of 3-D fields
+// flat = 1: a 2-D field riding in a batch of 3-D fields; zdone = 1: the z halos of the interior rows were already written
+// by the kernel that produced the field (corrector, tracer epilogue); zdone = 2: except the wall row Ny+1 of a Face-y field
+struct HaloSpec { float* a; int lx, ly, lz; float sign; int flat; int zdone; };
 
 // ---- multi-GPU halo exchange over peer-mapped (CUDA IPC) memory, one process per GPU (gb25_exchange.cu)
 // exported allocations: both halves of the double-buffered 3-D state (all tiles flip in lockstep, so a tile's current
@@ -60,8 +62,9 @@ struct gb25_handle {
   float* state_buf[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // [parity][u, v, T, S]
   int parity = 0;
   float* spec2d[4] = {nullptr, nullptr, nullptr, nullptr};   // speculative GU, GV, sum dz u*, sum dz v* (committed by launch_commit_spec)
-  struct { bool valid = false; float dt = 0.f, chi = 0.f; } spec;
+  struct { bool valid = false; float dt = 0.f, chi = 0.f; bool zhalo = false; } spec;
   bool use_spec = true;
+  bool use_zfold = true;               // corrector / tracer epilogue also write the z halos of the fields they produce
   // clock (model.clock)
   double time = 0.0;
   long iteration = 0;
@@ -109,7 +112,7 @@ struct StageScope {
   ~StageScope() { if (t) cudaEventRecord(t->ev[slot].second, h->stream); }
 };
 
-struct Ab2Spec { float dt, c1, c2; };   // AB2 epilogue of the tendency kernels: psi' = psi + dt (c1 Gn - c2 G-)
+struct Ab2Spec { float dt, c1, c2; int zhalo; };   // zhalo: the tracer epilogue also writes the (mirror) z halos of T', S'   // AB2 epilogue of the tendency kernels: psi' = psi + dt (c1 Gn - c2 G-)
 bool spec_possible(Handle* h);          // gb25_kernels.cu: the configuration runs the kernels that have the epilogue
 
 // stage launchers (gb25_kernels.cu)
@@ -144,7 +147,7 @@ void launch_correct_cache(Handle* h);
 void launch_barotropic_mode(Handle* h);
 void launch_ab2_fused(Handle* h, float dt, float chi);
 void launch_commit_spec(Handle* h);
-void launch_correct_fused(Handle* h);
+bool launch_correct_fused(Handle* h);   // true: it also wrote the z halos of u, v
 void launch_vdiff_explicit(Handle* h);
 void launch_implicit_columns(Handle* h, float dt, bool with_sums);
 bool launch_barotropic_persistent(Handle* h, float dt);   // gb25_baro.cu; false: not applicable, use the substep kernels

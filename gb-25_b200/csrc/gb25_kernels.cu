@@ -91,9 +91,9 @@ __global__ void k_halo_fold_row(DevGrid g, HaloBatch hb, int three_d) {
   a[row + i + g.Hx - 1] = sg * a[row + ip + g.Hx - 1];
 }
 // bottom/top: threads over (i, j, field)
-__global__ void k_halo_bottom_top(DevGrid g, HaloBatch hb) {
+__global__ void k_halo_bottom_top(DevGrid g, HaloBatch hb, int row0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  const int j = blockIdx.y + 1;
+  const int j = blockIdx.y + row0;
   const HaloField hf = hb.f[blockIdx.z];
   const int jt = g.Ny + ((hf.ly && g.wall_n) ? 1 : 0);
   if (i > g.Nx || j > jt || hf.flat) return;
@@ -149,9 +149,25 @@ void launch_halo_south_north(Handle* h, const HaloSpec* specs, int n, bool three
 }
 void launch_halo_bottom_top(Handle* h, const HaloSpec* specs, int n) {
   const DevGrid& g = h->g;
-  int maxlz; HaloBatch hb = make_batch(specs, n, &maxlz);
-  dim3 b1(128), g2((g.Nx + 127) / 128, g.Ny + 1, n);
-  k_halo_bottom_top<<<g2, b1, 0, h->stream>>>(g, hb); h->count_launch();
+  // fields whose producer already wrote the z halos drop out; of a Face-y field on a wall tile only the wall row is left
+  HaloSpec todo[9], wall[9]; int nt = 0, nw = 0;
+  for (int q = 0; q < n; q++) {
+    if (specs[q].flat) continue;
+    if (!specs[q].zdone) todo[nt++] = specs[q];
+    else if (specs[q].zdone == 2 && specs[q].ly && g.wall_n) wall[nw++] = specs[q];
+  }
+  int maxlz;
+  dim3 b1(128);
+  if (nt) {
+    HaloBatch hb = make_batch(todo, nt, &maxlz);
+    dim3 g2((g.Nx + 127) / 128, g.Ny + 1, nt);
+    k_halo_bottom_top<<<g2, b1, 0, h->stream>>>(g, hb, 1); h->count_launch();
+  }
+  if (nw) {
+    HaloBatch hb = make_batch(wall, nw, &maxlz);
+    dim3 g2((g.Nx + 127) / 128, 1, nw);
+    k_halo_bottom_top<<<g2, b1, 0, h->stream>>>(g, hb, g.Ny + 1); h->count_launch();
+  }
 }
 void launch_halo_periodic_x(Handle* h, const HaloSpec* specs, int n, bool three_d) {
   const DevGrid& g = h->g;
@@ -715,10 +731,14 @@ void launch_ab2_fused(Handle* h, float dt, float chi) {
 // barotropic tendencies) runs first in its own small kernel and leaves the unmasked transports in two scratch arrays,
 // from which the 3-D kernel recomputes the correction.
 #define CORR_KCH 10
+template <bool ZH>
 __global__ void __launch_bounds__(128) k_correct_3d(DevGrid g, DevFields f, const float* __restrict__ us2, const float* __restrict__ vs2,
-                                                    const float* __restrict__ ubar, const float* __restrict__ vbar) {
+                                                    const float* __restrict__ ubar, const float* __restrict__ vbar, int bottom_tile) {
   const int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x) + 1, j = blockIdx.y + 1;
   if (i > g.Nx) return;
+  // the impenetrable condition of the halo fill sets v(i, 1, k) = 0 on the bottom row of tiles right after this kernel; the
+  // z halos written here (ZH) must mirror that value, so it is applied now
+  const bool vwall = ZH && bottom_tile && j == 1;
   const int k0 = blockIdx.z * CORR_KCH + 1, k1 = min(k0 + CORR_KCH - 1, g.Nz);
   const int q2 = id2(g, i, j), n2 = g.n2;
   const float4 su = *reinterpret_cast<const float4*>(us2 + q2), sv = *reinterpret_cast<const float4*>(vs2 + q2);
@@ -751,8 +771,20 @@ __global__ void __launch_bounds__(128) k_correct_3d(DevGrid g, DevFields f, cons
         if (k <= kbv[c]) vn[c] = 0.f;
       }
     }
-    *reinterpret_cast<float4*>(f.u + q3) = make_float4(un[0], un[1], un[2], un[3]);
-    *reinterpret_cast<float4*>(f.v + q3) = make_float4(vn[0], vn[1], vn[2], vn[3]);
+    if (vwall) { vn[0] = 0.f; vn[1] = 0.f; vn[2] = 0.f; vn[3] = 0.f; }
+    const float4 uo = make_float4(un[0], un[1], un[2], un[3]), vo = make_float4(vn[0], vn[1], vn[2], vn[3]);
+    *reinterpret_cast<float4*>(f.u + q3) = uo;
+    *reinterpret_cast<float4*>(f.v + q3) = vo;
+    if (ZH) {   // no-flux z halos (mirror): psi(1-m) = psi(m), psi(Nz+m) = psi(Nz+1-m), m = 1..Hz  (k_halo_bottom_top)
+      if (k <= g.Hz) {
+        const size_t qm = q3 - (size_t)(2 * k - 1) * n2;
+        *reinterpret_cast<float4*>(f.u + qm) = uo; *reinterpret_cast<float4*>(f.v + qm) = vo;
+      }
+      if (k > g.Nz - g.Hz) {
+        const size_t qm = q3 + (size_t)(2 * (g.Nz - k) + 1) * n2;
+        *reinterpret_cast<float4*>(f.u + qm) = uo; *reinterpret_cast<float4*>(f.v + qm) = vo;
+      }
+    }
   }
 }
 // 2-D part of the corrector; leaves the unmasked transports in ubar / vbar for k_correct_3d
@@ -771,18 +803,23 @@ __global__ void k_correct_2d(DevGrid g, DevFields f, const float* __restrict__ u
   }
   f.gmU[q2] = f.gU[q2]; f.gmV[q2] = f.gV[q2];
 }
-void launch_correct_fused(Handle* h) {
+bool launch_correct_fused(Handle* h) {
   const DevGrid& g = h->g;
   static const bool streamed = []() { const char* e = getenv("GB25_CORRECT_3D"); return !(e && e[0] == '0'); }();
   if (streamed && g.Nx % 4 == 0 && g.Hx % 4 == 0 && g.PX % 4 == 0) {
     dim3 b2(128), g2((g.Nx + 127) / 128, g.Ny);
     k_correct_2d<<<g2, b2, 0, h->stream>>>(g, h->f, h->us2, h->vs2, h->corr_u, h->corr_v); h->count_launch();
     dim3 b(128), gr((g.Nx / 4 + 127) / 128, g.Ny, (g.Nz + CORR_KCH - 1) / CORR_KCH);
-    k_correct_3d<<<gr, b, 0, h->stream>>>(g, h->f, h->us2, h->vs2, h->corr_u, h->corr_v); h->count_launch();
-    return;
+    const bool zh = h->use_zfold && g.Nz >= g.Hz;
+    const int bottom = h->cfg.ry == 0 ? 1 : 0;
+    if (zh) k_correct_3d<true><<<gr, b, 0, h->stream>>>(g, h->f, h->us2, h->vs2, h->corr_u, h->corr_v, bottom);
+    else k_correct_3d<false><<<gr, b, 0, h->stream>>>(g, h->f, h->us2, h->vs2, h->corr_u, h->corr_v, bottom);
+    h->count_launch();
+    return zh;
   }
   dim3 b(128), gr((g.Nx + 127) / 128, g.Ny);
   k_correct_fused<<<gr, b, 0, h->stream>>>(g, h->f, h->us2, h->vs2); h->count_launch();
+  return false;
 }
 
 // =====================================================================================

@@ -719,7 +719,7 @@ k_mom_tma_p2(DevGrid g, const __grid_constant__ TmaMaps7 tm, const __grid_consta
 struct TmaMaps5 { CUtensorMap m[5]; };   // T, S, u, v, w
 // AB2 epilogue of the tracer kernel (template flag AB2): c' = mask(c + dt (c1 Gn - c2 G-)) into the other state buffer
 // (rows A9, A1: the arithmetic of k_ab2_ts_3d, bit for bit)
-struct TrAb2 { float* next[2]; float dt, c1, c2; };
+struct TrAb2 { float* next[2]; float dt, c1, c2; int zhalo; };
 struct TmaMaps2 { CUtensorMap m[2]; };   // G- of T and of S
 
 __device__ __forceinline__ float weno5_selp(const float* q, bool left, float eps) {   // q[0..5], face between q[2], q[3]
@@ -892,6 +892,10 @@ k_tracer_tma(DevGrid g, const __grid_constant__ TmaMaps5 tm, const __grid_consta
         float c0 = ab2_upd(W[r][0][3], ab.dt, ab2_g(ab.c1, ab.c2, gn.x, gmv.x)), c1n = ab2_upd(W[r][1][3], ab.dt, ab2_g(ab.c1, ab.c2, gn.y, gmv.y));
         if (g.immersed) { if (k <= kbc[r][0]) c0 = 0.f; if (k <= kbc[r][1]) c1n = 0.f; }
         *reinterpret_cast<float2*>(Tn + q3 + r * PX) = make_float2(c0, c1n);
+        if (ab.zhalo) {   // no-flux z halos of the updated tracer (the mirror of k_halo_bottom_top)
+          if (k <= g.Hz) *reinterpret_cast<float2*>(Tn + q3 + r * PX - (size_t)(2 * k - 1) * n2) = make_float2(c0, c1n);
+          if (k > Nz - g.Hz) *reinterpret_cast<float2*>(Tn + q3 + r * PX + (size_t)(2 * (Nz - k) + 1) * n2) = make_float2(c0, c1n);
+        }
       }
       const float2 a = __ldg(reinterpret_cast<const float2*>(T + q3 + (size_t)4 * n2 + r * PX));
 #pragma unroll
@@ -1034,7 +1038,7 @@ void launch_tracer_tendency_tma(Handle* h, const Ab2Spec* spec) {
   TrAb2 ab = {};
   TmaMaps2 tmg;
   tmg.m[0] = gm_map(t, h->f.gm[2], 2); tmg.m[1] = gm_map(t, h->f.gm[3], 3);
-  if (spec) ab = TrAb2{{h->state_buf[1 - par][2], h->state_buf[1 - par][3]}, spec->dt, spec->c1, spec->c2};
+  if (spec) ab = TrAb2{{h->state_buf[1 - par][2], h->state_buf[1 - par][3]}, spec->dt, spec->c1, spec->c2, spec->zhalo};
   StageScope ts(h, "kernel:k_tracer_tma");
   if (spec) k_tracer_tma<true><<<gr, b, sm, h->stream>>>(g, t->tr[par], tmg, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3], h->carry[2], h->carry[3], ab);
   else k_tracer_tma<false><<<gr, b, sm, h->stream>>>(g, t->tr[par], tmg, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3], h->carry[2], h->carry[3], ab);

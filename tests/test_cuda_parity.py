@@ -251,12 +251,14 @@ def test_ab2_epilogue_of_the_tendency_kernels_is_bit_identical(monkeypatch, grid
     ms = []
     for spec in ("1", "0"):
         monkeypatch.setenv("GB25_SPECULATE", spec)
+        monkeypatch.setenv("GB25_ZHALO_FOLD", spec)       # the second model also fills every z halo with k_halo_bottom_top
         m = M.baroclinic_instability_model(M.B200(0), Nx, Ny, Nz, Δt=60.0, grid_type=grid_type, physics=ph)
         M.set_baroclinic_instability(m)
         rng = np.random.default_rng(3)
         M.set(m, u=1e-3 * rng.random(m.interior("u").shape), v=1e-3 * rng.random(m.interior("v").shape))
         ms.append(m)
     monkeypatch.delenv("GB25_SPECULATE")
+    monkeypatch.delenv("GB25_ZHALO_FOLD")
 
     def same(tag):
         for n in STATE_FIELDS:
