@@ -345,28 +345,26 @@ def main():
     eta = model.interior("eta")
     finite = bool(np.isfinite(eta).all())
 
-    # ---- e2e: every step round-trips the prognostic state through pinned host buffers over the C ABI
+    # ---- e2e: every step round-trips the prognostic state through pinned host buffers over the C ABI, the way the
+    # reference moves state: set!(model, u=..., v=..., ...) writes interiors, Array(interior(psi)) reads them
     e2e = None
     if not args.no_e2e:
         names = ("u", "v", "T", "S", "eta", "U", "V")
-        host = {}
+        host = []
         for n in names:
-            shp = model.handle.field_shape(n)
-            tns = torch.empty(shp, dtype=torch.float32, pin_memory=True)
-            host[n] = tns.numpy()
-            model.handle.get_field(n, host[n])
-        nb = sum(a.nbytes for a in host.values())
+            tns = torch.empty(model.handle.interior_shape(n), dtype=torch.float32, pin_memory=True)
+            host.append(tns.numpy())
+        model.handle.get_fields(names, host, interior=True)
+        nb = sum(a.nbytes for a in host)
         ksteps = max(3, min(args.steps, 10))
         barrier()
         t0 = time.perf_counter()
         for _ in range(ksteps):
-            for n in names:
-                model.handle.set_field(n, host[n])
+            model.handle.set_fields(names, host, interior=True)
             if dist is not None:
                 dist.barrier()    # a tile's upload must be complete before a neighbour pushes halos into it
-            M.time_step(model)
-            for n in names:
-                model.handle.get_field(n, host[n])
+            M.time_step(model)             # (the uploaded state is the one just downloaded: halos and tendencies are current)
+            model.handle.get_fields(names, host, interior=True)
         barrier()
         el = time.perf_counter() - t0
         if dist is not None:
@@ -375,19 +373,22 @@ def main():
             el = float(t.item())
         e2e = {"value": cells_per_rank * world * ksteps / el, "unit": "cell-steps/s", "h2d_bytes_per_step": nb,
                "d2h_bytes_per_step": nb, "steps": ksteps,
-               "protocol": "per step: gb25_set_field(u,v,T,S,eta,U,V) from pinned host, gb25_time_step, gb25_get_field of the same"}
+               "protocol": "per step: gb25_set_fields(interiors of u,v,T,S,eta,U,V) from pinned host = set!(model, ...), "
+                           "gb25_time_step, gb25_get_fields(interiors) = Array(interior(psi)); "
+                           "one cudaMemcpy3DAsync per field, one synchronisation per batch"}
         # the reference's own usage (sync_states!, loop!(model, Ninner), compare_states): one upload, Ninner steps in one
         # host call, one download — reported beside the per-step protocol, not instead of it
         ninner = args.steps
+        phost = [torch.empty(model.handle.field_shape(n), dtype=torch.float32, pin_memory=True).numpy() for n in names]
+        model.handle.get_fields(names, phost)
+        pb = sum(a.nbytes for a in phost)
         barrier()
         t0 = time.perf_counter()
-        for n in names:
-            model.handle.set_field(n, host[n])
+        model.handle.set_fields(names, phost)
         if dist is not None:
             dist.barrier()
         M.loop(model, ninner)
-        for n in names:
-            model.handle.get_field(n, host[n])
+        model.handle.get_fields(names, phost)
         barrier()
         el = time.perf_counter() - t0
         if dist is not None:
@@ -395,8 +396,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             el = float(t.item())
         e2e["loop_protocol"] = {"value": cells_per_rank * world * ninner / el, "unit": "cell-steps/s", "steps": ninner,
-                                "h2d_bytes": nb, "d2h_bytes": nb,
-                                "protocol": "sync_states! (upload once), loop!(model, Ninner), download once; wall clock"}
+                                "h2d_bytes": pb, "d2h_bytes": pb,
+                                "protocol": "sync_states! (parents uploaded once), loop!(model, Ninner), download once; wall clock"}
 
     if rank != 0:
         if dist is not None:

@@ -355,27 +355,44 @@ extern "C" int gb25_field_shape(const gb25_handle* h, int field, int shape[3]) {
   parent_shape(h, field, shape);
   return GB25_OK;
 }
-static int copy_field(Handle* h, int field, float* host, bool to_device, bool sync = true) {
+static void interior_shape(const Handle* h, int field, int shape[3]) {
+  const FieldInfo& fi = kFieldInfo[field];
+  const gb25_config& c = h->cfg;
+  shape[0] = c.Nx;
+  shape[1] = c.Ny + ((fi.ly && h->g.wall_n) ? 1 : 0);
+  shape[2] = fi.three_d ? c.Nz + fi.lz : 1;
+}
+extern "C" int gb25_interior_shape(const gb25_handle* h, int field, int shape[3]) {
+  if (!h || field < 0 || field >= GB25_FIELD_COUNT || !shape) return GB25_ERR_INVALID;
+  interior_shape(h, field, shape);
+  return GB25_OK;
+}
+// one pitched 3-D copy between a host array (parent or interior shape) and the internal (PX, PY, PZ) layout
+static int copy_field(Handle* h, int field, float* host, bool to_device, bool interior = false, bool sync = true) {
   if (field < 0 || field >= GB25_FIELD_COUNT || !host) { h->err = "bad field id or null buffer"; return GB25_ERR_INVALID; }
   int s[3];
-  parent_shape(h, field, s);
+  if (interior) interior_shape(h, field, s); else parent_shape(h, field, s);
   const DevGrid& g = h->g;
+  const bool three_d = kFieldInfo[field].three_d;
   cudaMemcpy3DParms p = {};
   p.extent = make_cudaExtent((size_t)s[0] * sizeof(float), s[1], s[2]);
   cudaPitchedPtr hp = make_cudaPitchedPtr(host, (size_t)s[0] * sizeof(float), s[0], s[1]);
   cudaPitchedPtr dp = make_cudaPitchedPtr(h->field_ptr[field], (size_t)g.PX * sizeof(float), g.PX, g.PY);
-  if (to_device) { p.srcPtr = hp; p.dstPtr = dp; p.kind = cudaMemcpyHostToDevice; }
-  else { p.srcPtr = dp; p.dstPtr = hp; p.kind = cudaMemcpyDeviceToHost; }
+  const cudaPos dpos = interior ? make_cudaPos((size_t)g.Hx * sizeof(float), g.Hy, three_d ? g.Hz : 0) : make_cudaPos(0, 0, 0);
+  if (to_device) { p.srcPtr = hp; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
+  else { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.kind = cudaMemcpyDeviceToHost; }
   CK(h, cudaMemcpy3DAsync(&p, h->stream));
   if (to_device) {
     h->spec.valid = false;
     // the other half of a double-buffered field receives the same parent, so that halo cells no fill ever writes
     // (y-z corners, the rows behind an impenetrable wall) hold the uploaded values whichever buffer is current
-    for (int q = 0; q < 4; q++)
-      if (h->field_ptr[field] == h->state_buf[h->parity][q]) {
-        p.dstPtr = make_cudaPitchedPtr(h->state_buf[1 - h->parity][q], (size_t)g.PX * sizeof(float), g.PX, g.PY);
-        CK(h, cudaMemcpy3DAsync(&p, h->stream));
-      }
+    // (an interior upload touches no halo cell, and the other half's interior is rewritten before it is read)
+    if (!interior)
+      for (int q = 0; q < 4; q++)
+        if (h->field_ptr[field] == h->state_buf[h->parity][q]) {
+          p.dstPtr = make_cudaPitchedPtr(h->state_buf[1 - h->parity][q], (size_t)g.PX * sizeof(float), g.PX, g.PY);
+          CK(h, cudaMemcpy3DAsync(&p, h->stream));
+        }
   }
   if (sync) CK(h, cudaStreamSynchronize(h->stream));
   return GB25_OK;
@@ -387,6 +404,34 @@ extern "C" int gb25_set_field(gb25_handle* h, int field, const float* host_paren
 extern "C" int gb25_get_field(gb25_handle* h, int field, float* host_parent) {
   REQUIRE(h);
   return copy_field(h, field, host_parent, false);
+}
+extern "C" int gb25_set_interior(gb25_handle* h, int field, const float* host_interior) {
+  REQUIRE(h);
+  return copy_field(h, field, const_cast<float*>(host_interior), true, true);
+}
+extern "C" int gb25_get_interior(gb25_handle* h, int field, float* host_interior) {
+  REQUIRE(h);
+  return copy_field(h, field, host_interior, false, true);
+}
+extern "C" int gb25_set_fields(gb25_handle* h, int n, const int* fields, const float* const* host, int interior) {
+  REQUIRE(h);
+  if (n < 0 || (n && (!fields || !host))) { h->err = "gb25_set_fields: null argument"; return GB25_ERR_INVALID; }
+  for (int q = 0; q < n; q++) {
+    const int rc = copy_field(h, fields[q], const_cast<float*>(host[q]), true, interior != 0, false);
+    if (rc != GB25_OK) return rc;
+  }
+  CK(h, cudaStreamSynchronize(h->stream));     // the host buffers are borrowed for the duration of the call only
+  return GB25_OK;
+}
+extern "C" int gb25_get_fields(gb25_handle* h, int n, const int* fields, float* const* host, int interior) {
+  REQUIRE(h);
+  if (n < 0 || (n && (!fields || !host))) { h->err = "gb25_get_fields: null argument"; return GB25_ERR_INVALID; }
+  for (int q = 0; q < n; q++) {
+    const int rc = copy_field(h, fields[q], host[q], false, interior != 0, false);
+    if (rc != GB25_OK) return rc;
+  }
+  CK(h, cudaStreamSynchronize(h->stream));
+  return GB25_OK;
 }
 extern "C" int gb25_set_clock(gb25_handle* h, double time, long iteration, float last_dt) {
   if (!h) return GB25_ERR_INVALID;

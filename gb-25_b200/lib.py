@@ -38,6 +38,7 @@ FIELD_LOC = {
 EXPORTED_SYMBOLS = (
     "gb25_abi_version", "gb25_create", "gb25_destroy", "gb25_last_error", "gb25_clear_error",
     "gb25_field_shape", "gb25_set_field", "gb25_get_field", "gb25_set_clock", "gb25_get_clock",
+    "gb25_interior_shape", "gb25_set_interior", "gb25_get_interior", "gb25_set_fields", "gb25_get_fields",
     "gb25_initialize", "gb25_update_state", "gb25_first_time_step", "gb25_time_step", "gb25_loop",
     "gb25_synchronize", "gb25_mask_immersed_fields", "gb25_fill_halo_regions", "gb25_compute_auxiliaries",
     "gb25_compute_tendencies", "gb25_compute_momentum_tendencies", "gb25_compute_tracer_tendencies",
@@ -95,6 +96,11 @@ def load():
     lib.gb25_field_shape.argtypes = [H, C.c_int, C.POINTER(C.c_int)]
     lib.gb25_set_field.argtypes = [H, C.c_int, C.c_void_p]
     lib.gb25_get_field.argtypes = [H, C.c_int, C.c_void_p]
+    lib.gb25_interior_shape.argtypes = [H, C.c_int, C.POINTER(C.c_int)]
+    lib.gb25_set_interior.argtypes = [H, C.c_int, C.c_void_p]
+    lib.gb25_get_interior.argtypes = [H, C.c_int, C.c_void_p]
+    lib.gb25_set_fields.argtypes = [H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_int]
+    lib.gb25_get_fields.argtypes = [H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_int]
     lib.gb25_set_clock.argtypes = [H, C.c_double, C.c_long, C.c_float]
     lib.gb25_get_clock.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_float)]
     lib.gb25_first_time_step.argtypes = [H, C.c_float]
@@ -188,6 +194,40 @@ class Handle:
             out = np.empty(self.field_shape(name), dtype=np.float32)
         self.check(self.lib.gb25_get_field(self.h, FIELD_ID[name], out.ctypes.data))
         return out
+
+    def interior_shape(self, name):
+        s = (C.c_int * 3)()
+        self.check(self.lib.gb25_interior_shape(self.h, FIELD_ID[name], s))
+        return (s[2], s[1], s[0])
+
+    def set_interior(self, name, values):
+        """set!(model, name=values): interior-shaped upload, halos untouched."""
+        shp = self.interior_shape(name)
+        a = _f32(np.broadcast_to(np.asarray(values, dtype=np.float32), shp))
+        self.check(self.lib.gb25_set_interior(self.h, FIELD_ID[name], a.ctypes.data))
+
+    def get_interior(self, name, out=None):
+        if out is None:
+            out = np.empty(self.interior_shape(name), dtype=np.float32)
+        self.check(self.lib.gb25_get_interior(self.h, FIELD_ID[name], out.ctypes.data))
+        return out
+
+    def _batch(self, fn, names, arrays, interior):
+        n = len(names)
+        ids = (C.c_int * n)(*[FIELD_ID[x] for x in names])
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
+        for x, a in zip(names, arrays):
+            want = self.interior_shape(x) if interior else self.field_shape(x)
+            if a.shape != want or a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"{x}: need a C-contiguous float32 array of shape {want}")
+        self.check(fn(self.h, n, ids, ptrs, 1 if interior else 0))
+
+    def set_fields(self, names, arrays, interior=False):
+        """Batched upload: one cudaMemcpy3DAsync per field, one synchronisation."""
+        self._batch(self.lib.gb25_set_fields, names, arrays, interior)
+
+    def get_fields(self, names, arrays, interior=False):
+        self._batch(self.lib.gb25_get_fields, names, arrays, interior)
 
     def set_clock(self, time, iteration, last_dt):
         self.check(self.lib.gb25_set_clock(self.h, time, iteration, last_dt))

@@ -102,6 +102,12 @@ class HydrostaticFreeSurfaceModel(ModelBase):
     def set_parent(self, name, a):
         self.handle.set_field(name, a)
 
+    def interior(self, name):                  # Array(interior(ψ)): one strided device-to-host copy
+        return self.handle.get_interior(name)
+
+    def set_interior(self, name, values):      # set!(model, name=values)
+        self.handle.set_interior(name, values)
+
     def _push_clock(self):
         dt = self.clock.last_Δt
         self.handle.set_clock(self.clock.time, self.clock.iteration, 0.0 if math.isinf(dt) else dt)

@@ -112,6 +112,18 @@ int gb25_clear_error(gb25_handle* h);
 int gb25_field_shape(const gb25_handle* h, int field, int shape[3]);
 int gb25_set_field(gb25_handle* h, int field, const float* host_parent);
 int gb25_get_field(gb25_handle* h, int field, float* host_parent);
+/* Interior-shaped transfers: what Oceananigans' set!(model, u=..., v=...) writes and Array(interior(ψ)) reads
+ * (correctness/correctness_baroclinic_instability_simulation_run.jl:40-42; src/model_utils.jl:99-131 for T, S).
+ * The host array has the interior shape of the field — (Nx, Ny, Nz) for a (C,C,C) field, Ny+1 rows for a Face-y field
+ * on a tile that owns the north wall of a Bounded grid, Nz+1 levels for w, one level for 2-D fields — and halos are
+ * left untouched.  gb25_interior_shape returns it. */
+int gb25_interior_shape(const gb25_handle* h, int field, int shape[3]);
+int gb25_set_interior(gb25_handle* h, int field, const float* host_interior);
+int gb25_get_interior(gb25_handle* h, int field, float* host_interior);
+/* Batched transfers: n fields, all copies enqueued back to back on the handle's stream (one cudaMemcpy3DAsync per
+ * field) and ONE synchronisation at the end.  interior = 0: parent shape, 1: interior shape. */
+int gb25_set_fields(gb25_handle* h, int n, const int* fields, const float* const* host, int interior);
+int gb25_get_fields(gb25_handle* h, int n, const int* fields, float* const* host, int interior);
 /* model.clock: time, iteration, last_Δt (src/baroclinic_instability_model.jl:82) */
 int gb25_set_clock(gb25_handle* h, double time, long iteration, float last_dt);
 int gb25_get_clock(const gb25_handle* h, double* time, long* iteration, float* last_dt);

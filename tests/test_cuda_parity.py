@@ -67,6 +67,41 @@ def test_set_get_roundtrip_all_fields_bit_exact(oracle_mod, grid_type, Nx, Ny, N
         assert np.array_equal(rm.parent(n), a)
 
 
+@pytest.mark.parametrize("grid_type,Nx,Ny,Nz", GRIDS)
+def test_interior_and_batched_transfers(oracle_mod, grid_type, Nx, Ny, Nz):
+    """gb25_set_interior / gb25_get_interior (set!, Array(interior(psi))) and the batched gb25_set_fields / gb25_get_fields
+    move exactly the bytes the parent-shaped calls move: interiors land inside the parent, halos are untouched."""
+    rm, vm = make_models(grid_type, Nx, Ny, Nz, 60.0, oracle_mod)
+    rng = np.random.default_rng(5)
+    names = [n for n in STATE_FIELDS]
+    for n in names:
+        par = rng.standard_normal(rm.handle.field_shape(n)).astype(np.float32)
+        rm.set_parent(n, par)
+        ishp = rm.handle.interior_shape(n)
+        assert ishp == M.ModelBase.interior(vm, n).shape, n                  # the mirror's slice of the parent
+        inner = rng.standard_normal(ishp).astype(np.float32)
+        rm.handle.set_interior(n, inner)
+        sl = M._interior_slices(rm.grid, M.FIELD_LOC[n])
+        want = par.copy(); want[sl] = inner
+        assert np.array_equal(rm.parent(n), want), n
+        assert np.array_equal(rm.handle.get_interior(n), inner), n
+    pars = [np.ascontiguousarray(rng.standard_normal(rm.handle.field_shape(n)).astype(np.float32)) for n in names]
+    rm.handle.set_fields(names, pars)
+    outs = [np.empty_like(a) for a in pars]
+    rm.handle.get_fields(names, outs)
+    for n, a, b in zip(names, pars, outs):
+        assert np.array_equal(a, b), n
+    inner = [np.ascontiguousarray(rng.standard_normal(rm.handle.interior_shape(n)).astype(np.float32)) for n in names]
+    rm.handle.set_fields(names, inner, interior=True)
+    outs = [np.empty_like(a) for a in inner]
+    rm.handle.get_fields(names, outs, interior=True)
+    for n, a, b, par in zip(names, inner, outs, pars):
+        assert np.array_equal(a, b), n
+        want = par.copy(); want[M._interior_slices(rm.grid, M.FIELD_LOC[n])] = a
+        assert np.array_equal(rm.parent(n), want), n
+    rm.close()
+
+
 def _assert_close(rm, vm, names, rtol=RTOL, elementwise=None, halos=True):
     bad = []
     for n in names:
