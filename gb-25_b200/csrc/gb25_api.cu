@@ -486,6 +486,7 @@ static void stage_tend(Handle* h, const Ab2Spec* spec = nullptr) {
   { StageScope t(h, "momentum_tendencies"); launch_momentum_tendency(h, spec); }
   { StageScope t(h, "tracer_tendencies"); launch_tracer_tendency(h, spec); }
   if (h->cfg.closure == 1) { StageScope t(h, "vertical_diffusion"); launch_vdiff_explicit(h); }
+  if (h->has_bflux) { StageScope t(h, "boundary_tendencies"); launch_boundary_tendencies(h); }
 }
 static void stage_update_state(Handle* h) {
   stage_mask(h);
@@ -609,6 +610,35 @@ extern "C" int gb25_compute_tracer_tendencies(gb25_handle* h) {
   h->spec.valid = false;
   { StageScope t(h, "tracer_tendencies"); launch_tracer_tendency(h); }
   return check_async(h, "gb25_compute_tracer_tendencies");
+}
+extern "C" int gb25_compute_boundary_tendencies(gb25_handle* h) {
+  REQUIRE(h);
+  h->spec.valid = false;
+  { StageScope t(h, "boundary_tendencies"); launch_boundary_tendencies(h); }
+  return check_async(h, "gb25_compute_boundary_tendencies");
+}
+extern "C" int gb25_set_flux_boundary_condition(gb25_handle* h, int field, int side, const float* flux) {
+  REQUIRE(h);
+  int q = -1;
+  if (field == GB25_U) q = 0; else if (field == GB25_V) q = 1; else if (field == GB25_T) q = 2; else if (field == GB25_S) q = 3;
+  if (q < 0 || side < 0 || side > 1) { h->err = "gb25_set_flux_boundary_condition: field must be GB25_U/V/T/S, side 0 (bottom) or 1 (top)"; return GB25_ERR_INVALID; }
+  h->spec.valid = false;
+  CK(h, cudaStreamSynchronize(h->stream));
+  if (!flux) {
+    h->bflux[q][side] = nullptr;      // (the allocation stays in h->allocs until gb25_destroy)
+  } else {
+    int s[3];
+    parent_shape(h, field == GB25_V ? GB25_BARO_V : (field == GB25_U ? GB25_BARO_U : GB25_ETA), s);   // 2-D parent of that staggering
+    float* d = nullptr;
+    CK(h, cudaMalloc(&d, (size_t)h->g.n2 * sizeof(float)));
+    h->allocs.push_back(d);
+    CK(h, cudaMemset(d, 0, (size_t)h->g.n2 * sizeof(float)));
+    CK(h, cudaMemcpy2D(d, (size_t)h->g.PX * sizeof(float), flux, (size_t)s[0] * sizeof(float), (size_t)s[0] * sizeof(float), s[1], cudaMemcpyHostToDevice));
+    h->bflux[q][side] = d;
+  }
+  h->has_bflux = false;
+  for (int a = 0; a < 4; a++) for (int b = 0; b < 2; b++) h->has_bflux |= h->bflux[a][b] != nullptr;
+  return GB25_OK;
 }
 extern "C" int gb25_ab2_step(gb25_handle* h, float dt, float chi) {
   REQUIRE(h);

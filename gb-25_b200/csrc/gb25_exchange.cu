@@ -302,21 +302,51 @@ void exchange_baro_uv(Handle* h) {    // after the U,V kernel: the eta kernel re
 // --------------------------------------------------------------------------------- C ABI
 extern "C" int gb25_exchange_blob_size(void) { return (int)sizeof(ExBlob); }
 
+// the windows a tile offers to its neighbours besides its fields: the flag / pair-inbox buffer and the column inbox
+static int exchange_alloc_windows(Handle* h) {
+  Exchange& X = h->ex;
+  if (!X.flags) {
+    // a dedicated 2 MiB allocation so that the IPC handle maps exactly this buffer
+    if (cudaMalloc(&X.flags, 2 << 20) != cudaSuccess) { h->err = "exchange: cudaMalloc flags"; return GB25_ERR_ALLOC; }
+    cudaMemset(X.flags, 0, 2 << 20);
+  }
+  if (!X.xbox) {
+    X.xbox_stride = (size_t)9 * h->g.PZ * h->g.PY * h->g.Hx;
+    if (cudaMalloc(&X.xbox, 4 * X.xbox_stride * sizeof(float)) != cudaSuccess) { h->err = "exchange: cudaMalloc column inbox"; return GB25_ERR_ALLOC; }
+    cudaMemset(X.xbox, 0, 4 * X.xbox_stride * sizeof(float));
+  }
+  return GB25_OK;
+}
+// ranks of the tiles this tile exchanges with, by slot (-1: none)
+static void exchange_neighbours(const gb25_config& c, int want[EX_NSLOT]) {
+  auto rk = [&](int rx, int ry) { return ((rx % c.Rx) + c.Rx) % c.Rx + c.Rx * ry; };
+  for (int s = 0; s < EX_NSLOT; s++) want[s] = -1;
+  if (c.Rx > 1) { want[SLOT_W] = rk(c.rx - 1, c.ry); want[SLOT_E] = rk(c.rx + 1, c.ry); }
+  if (c.ry > 0) want[SLOT_S] = rk(c.rx, c.ry - 1);
+  if (c.ry < c.Ry - 1) want[SLOT_N] = rk(c.rx, c.ry + 1);
+  if (c.topo_y == GB25_TOPO_FOLD && c.ry == c.Ry - 1 && c.Rx > 1) {
+    want[SLOT_FOLD] = rk(c.Rx - 1 - c.rx, c.ry);
+    want[SLOT_FOLD2] = rk(c.Rx - c.rx, c.ry);
+  }
+}
+static int exchange_finish_connect(Handle* h) {
+  Exchange& X = h->ex;
+  // A reconnect restarts every sequence number, so the flag words and the pair inbox must not keep values of the previous
+  // session (a stale number would satisfy a wait).  The caller synchronises all ranks before reconnecting and puts a
+  // barrier after it (distributed.connect), so no neighbour writes into this buffer while it is cleared.
+  if (cudaMemset(X.flags, 0, 2 << 20) != cudaSuccess) { h->err = "exchange connect: cudaMemset flags"; return GB25_ERR_CUDA; }
+  X.seq = 0; X.xseq = 0;
+  X.on = true;
+  baro_plan_free(h);   // the persistent substep kernel restarts its sequence numbers on the (zeroed) shared flag buffer
+  return GB25_OK;
+}
+
 extern "C" int gb25_exchange_export(gb25_handle* h, void* blob) {
   if (!h || !blob) return GB25_ERR_INVALID;
   cudaSetDevice(h->device);
   ExBlob b; memset(&b, 0, sizeof b);
   Exchange& X = h->ex;
-  if (!X.flags) {
-    // a dedicated 2 MiB allocation so that the IPC handle maps exactly this buffer
-    if (cudaMalloc(&X.flags, 2 << 20) != cudaSuccess) { h->err = "gb25_exchange_export: cudaMalloc flags"; return GB25_ERR_ALLOC; }
-    cudaMemset(X.flags, 0, 2 << 20);
-  }
-  if (!X.xbox) {
-    X.xbox_stride = (size_t)9 * h->g.PZ * h->g.PY * h->g.Hx;
-    if (cudaMalloc(&X.xbox, 4 * X.xbox_stride * sizeof(float)) != cudaSuccess) { h->err = "gb25_exchange_export: cudaMalloc column inbox"; return GB25_ERR_ALLOC; }
-    cudaMemset(X.xbox, 0, 4 * X.xbox_stride * sizeof(float));
-  }
+  { const int rc = exchange_alloc_windows(h); if (rc != GB25_OK) return rc; }
   float* tab[EX_NF];
   exchange_table(h, tab);
   for (int q = 0; q < EX_NF; q++) {
@@ -345,16 +375,8 @@ extern "C" int gb25_exchange_connect(gb25_handle* h, const void* blobs, int nran
     if (B[r].rank != r || B[r].Nx != c.Nx || B[r].Ny != c.Ny || B[r].Nz != c.Nz || B[r].Rx != c.Rx || B[r].Ry != c.Ry) {
       h->err = "gb25_exchange_connect: blobs must be ordered by rank and describe equal tiles"; return GB25_ERR_INVALID;
     }
-  auto rk = [&](int rx, int ry) { return ((rx % c.Rx) + c.Rx) % c.Rx + c.Rx * ry; };
   int want[EX_NSLOT];
-  for (int s = 0; s < EX_NSLOT; s++) want[s] = -1;
-  if (c.Rx > 1) { want[SLOT_W] = rk(c.rx - 1, c.ry); want[SLOT_E] = rk(c.rx + 1, c.ry); }
-  if (c.ry > 0) want[SLOT_S] = rk(c.rx, c.ry - 1);
-  if (c.ry < c.Ry - 1) want[SLOT_N] = rk(c.rx, c.ry + 1);
-  if (c.topo_y == GB25_TOPO_FOLD && c.ry == c.Ry - 1 && c.Rx > 1) {
-    want[SLOT_FOLD] = rk(c.Rx - 1 - c.rx, c.ry);
-    want[SLOT_FOLD2] = rk(c.Rx - c.rx, c.ry);
-  }
+  exchange_neighbours(c, want);
   // map every distinct peer once
   std::vector<ExPeer> mapped(nranks);
   std::vector<char> have(nranks, 0);
@@ -385,13 +407,72 @@ extern "C" int gb25_exchange_connect(gb25_handle* h, const void* blobs, int nran
     }
     X.to[s] = mapped[r];
   }
-  // A reconnect restarts every sequence number, so the flag words and the pair inbox must not keep values of the previous
-  // session (a stale number would satisfy a wait).  The caller synchronises all ranks before reconnecting and puts a
-  // barrier after it (distributed.connect), so no neighbour writes into this buffer while it is cleared.
-  if (cudaMemset(X.flags, 0, 2 << 20) != cudaSuccess) { h->err = "gb25_exchange_connect: cudaMemset flags"; return GB25_ERR_CUDA; }
-  X.seq = 0; X.xseq = 0;
-  X.on = true;
-  baro_plan_free(h);   // the persistent substep kernel restarts its sequence numbers on the (zeroed) shared flag buffer
+  return exchange_finish_connect(h);
+}
+
+// Single process, one handle per device (the reference drives all GPUs of a node from one process:
+// /root/reference/sharding/sharded_baroclinic_instability_simulation_run.jl:49, `single_gpu_per_process=false`).  No IPC:
+// after cudaDeviceEnablePeerAccess the neighbours' allocations are ordinary device pointers.  handles[r] is the tile of
+// rank r = rx + Rx*ry.  Every tile must live on its own device: the persistent substep kernels of neighbouring tiles wait
+// for one another and must be co-resident.
+extern "C" int gb25_exchange_connect_local(gb25_handle** hs, int n) {
+  if (!hs || n < 1) return GB25_ERR_INVALID;
+  for (int r = 0; r < n; r++) if (!hs[r]) return GB25_ERR_INVALID;
+  Handle* h0 = hs[0];
+  const gb25_config& c0 = h0->cfg;
+  if (n != c0.Rx * c0.Ry) { h0->err = "gb25_exchange_connect_local: n != Rx*Ry"; return GB25_ERR_INVALID; }
+  for (int r = 0; r < n; r++) {
+    const gb25_config& c = hs[r]->cfg;
+    if (c.rx + c.Rx * c.ry != r || c.Nx != c0.Nx || c.Ny != c0.Ny || c.Nz != c0.Nz || c.Rx != c0.Rx || c.Ry != c0.Ry) {
+      h0->err = "gb25_exchange_connect_local: handles must be ordered by rank and describe equal tiles"; return GB25_ERR_INVALID;
+    }
+    if (c.fold_variant == 1 && c.Rx > 1 && c.topo_y == GB25_TOPO_FOLD) { h0->err = "gb25_exchange_connect_local: fold_variant 1 is only implemented for Rx == 1"; return GB25_ERR_INVALID; }
+    for (int q = 0; q < r; q++)
+      if (hs[q]->device == hs[r]->device) { h0->err = "gb25_exchange_connect_local: every tile needs its own device"; return GB25_ERR_INVALID; }
+  }
+  for (int r = 0; r < n; r++) {
+    cudaSetDevice(hs[r]->device);
+    cudaStreamSynchronize(hs[r]->stream);
+    const int rc = exchange_alloc_windows(hs[r]);
+    if (rc != GB25_OK) { h0->err = hs[r]->err; return rc; }
+    for (int q = 0; q < n; q++) {
+      if (q == r) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, hs[r]->device, hs[q]->device);
+      if (!can) { h0->err = "gb25_exchange_connect_local: devices cannot access each other's memory"; return GB25_ERR_COMM; }
+      const cudaError_t e = cudaDeviceEnablePeerAccess(hs[q]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { h0->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return GB25_ERR_COMM; }
+      cudaGetLastError();
+    }
+  }
+  for (int r = 0; r < n; r++) {
+    Handle* h = hs[r];
+    Exchange& X = h->ex;
+    X.nranks = n; X.rank = r;
+    int want[EX_NSLOT];
+    exchange_neighbours(h->cfg, want);
+    for (int s = 0; s < EX_NSLOT; s++) {
+      X.to[s].rank = want[s];
+      if (want[s] < 0) continue;
+      Handle* p = hs[want[s]];
+      exchange_table(p, X.to[s].fld);
+      X.to[s].flags = p->ex.flags;
+    }
+    cudaSetDevice(h->device);
+    const int rc = exchange_finish_connect(h);
+    if (rc != GB25_OK) { h0->err = h->err; return rc; }
+  }
+  return GB25_OK;
+}
+// One loop over all tiles of a single-process partition: every step is enqueued on every device before the next one, so no
+// device's launch queue fills up with work that waits for a neighbour whose step has not been enqueued yet.
+extern "C" int gb25_loop_all(gb25_handle** hs, int n, float dt, int nsteps) {
+  if (!hs || n < 1 || nsteps < 0) return GB25_ERR_INVALID;
+  for (int s = 0; s < nsteps; s++)
+    for (int r = 0; r < n; r++) {
+      const int rc = gb25_time_step(hs[r], dt);
+      if (rc != GB25_OK) return rc;
+    }
   return GB25_OK;
 }
 

@@ -65,6 +65,9 @@ struct gb25_handle {
   struct { bool valid = false; float dt = 0.f, chi = 0.f; bool zhalo = false; } spec;
   bool use_spec = true;
   bool use_zfold = true;               // corrector / tracer epilogue also write the z halos of the fields they produce
+  // flux boundary conditions (row A7): 2-D device arrays [u, v, T, S][bottom, top], nullptr = no-flux
+  float* bflux[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  bool has_bflux = false;
   // clock (model.clock)
   double time = 0.0;
   long iteration = 0;
@@ -149,6 +152,7 @@ void launch_ab2_fused(Handle* h, float dt, float chi);
 void launch_commit_spec(Handle* h);
 bool launch_correct_fused(Handle* h);   // true: it also wrote the z halos of u, v
 void launch_vdiff_explicit(Handle* h);
+void launch_boundary_tendencies(Handle* h);
 void launch_implicit_columns(Handle* h, float dt, bool with_sums);
 bool launch_barotropic_persistent(Handle* h, float dt);   // gb25_baro.cu; false: not applicable, use the substep kernels
 void baro_plan_free(Handle* h);

@@ -366,6 +366,7 @@ void launch_tracer_tendency_v1(Handle* h) {
 }
 bool spec_possible(Handle* h) {
   return h->use_spec && h->use_fused && h->use_tma && h->use_tma_tracer && h->use_packed && h->g.Nx % 4 == 0 && h->cfg.closure != 1 &&
+         !h->has_bflux &&     // (flux boundary conditions are added to Gn after the tendency kernels)
          tma_available(h);
 }
 void launch_tracer_tendency(Handle* h, const Ab2Spec* spec) {
@@ -855,6 +856,37 @@ void launch_vdiff_explicit(Handle* h) {
   const DevGrid& g = h->g;
   dim3 b(128), gr((g.Nx + 127) / 128, g.Ny, g.Nz);
   k_vdiff_explicit<<<gr, b, 0, h->stream>>>(g, h->f, h->cfg.kappa, h->cfg.nu); h->count_launch();
+}
+// =====================================================================================
+// Boundary tendency contributions (row A7): compute_hydrostatic_boundary_tendency_contributions! -> apply_z_bcs!
+// (/root/reference/src/precompile.jl:52-61).  Gc[i,j,1] += J_bottom Az / V, Gc[i,j,Nz] -= J_top Az / V, Az and V at the
+// location of the field; only fields with a flux array set take part.
+// =====================================================================================
+struct FluxSet { const float* a[4][2]; };
+__global__ void k_boundary_tendencies(DevGrid g, DevFields f, FluxSet fs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1, j = blockIdx.y + 1;
+  if (i > g.Nx) return;
+  const int q2 = id2(g, i, j);
+  const float* az[4] = {g.azfc, g.azcf, g.azcc, g.azcc};
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+      if (!fs.a[q][side]) continue;
+      const int k = side ? g.Nz : 1;
+      const size_t q3 = q2 + (size_t)g.n2 * (k + g.Hz - 1);
+      const float A = az[q][q2], V = A * g.dzc[k + g.Hz - 1];
+      const float d = fs.a[q][side][q2] * A / V;
+      f.gn[q][q3] = side ? f.gn[q][q3] - d : f.gn[q][q3] + d;
+    }
+}
+void launch_boundary_tendencies(Handle* h) {
+  if (!h->has_bflux) return;
+  const DevGrid& g = h->g;
+  FluxSet fs;
+  for (int q = 0; q < 4; q++) for (int s = 0; s < 2; s++) fs.a[q][s] = h->bflux[q][s];
+  dim3 b(128), gr((g.Nx + 127) / 128, g.Ny);
+  k_boundary_tendencies<<<gr, b, 0, h->stream>>>(g, h->f, fs); h->count_launch();
 }
 // implicit: (I - dt d_z K d_z) c = c*, Thomas algorithm per column (Oceananigans' batched tridiagonal solver);
 // the elimination factors t[k] go through a 3-D scratch array (the zeta scratch, rebuilt later in the step)

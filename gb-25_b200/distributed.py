@@ -109,6 +109,76 @@ def barrier(model):
     model.dist.barrier()
 
 
+# ------------------------------------------------------------------------------------------------
+# One process driving every GPU of the node (the reference's `single_gpu_per_process=false`,
+# /root/reference/sharding/sharded_baroclinic_instability_simulation_run.jl:49): a list of tile models, one per device,
+# connected with gb25_exchange_connect_local; every stepping call is issued for all tiles before any is synchronised.
+# ------------------------------------------------------------------------------------------------
+class LocalPartition:
+    def __init__(self, Nx, Ny, Nz, *, Δt, grid_type="simple_lat_lon", devices=(0, 1), Rx=None, Ry=None, halo=(8, 8, 8),
+                 physics=None, global_size=False):
+        n = len(devices)
+        if Rx is None:
+            Rx, Ry = factors(n)
+        if Rx * Ry != n:
+            raise ValueError(f"partition {Rx}x{Ry} does not match {n} devices")
+        gNx, gNy = (Nx, Ny) if global_size else (Nx * Rx, Ny * Ry)
+        self.global_grid = M.make_grid(gNx, gNy, Nz, halo, grid_type)
+        self.Rx, self.Ry = Rx, Ry
+        self.models = []
+        for r, dev in enumerate(devices):
+            rx, ry = rank_coords(r, Rx, Ry)
+            m = M.HydrostaticFreeSurfaceModel(M.B200(dev), tile_grid(self.global_grid, Rx, Ry, rx, ry), physics,
+                                              partition=(Rx, Ry, rx, ry))
+            m.partition = (Rx, Ry, rx, ry)
+            m.clock.last_Δt = float(np.float32(Δt))
+            self.models.append(m)
+        self.lib = self.models[0].handle.lib
+        self._hs = (C.c_void_p * n)(*[m.handle.h for m in self.models])
+        if n > 1:
+            self.models[0].handle.check(self.lib.gb25_exchange_connect_local(self._hs, n))
+
+    def _each(self, fn):
+        for m in self.models:
+            fn(m)
+
+    def first_time_step(self): self._each(M.first_time_step)
+    def time_step(self): self._each(M.time_step)
+    def update_state(self): self._each(M.update_state)
+
+    def loop(self, Ninner):
+        m0 = self.models[0]
+        for m in self.models:
+            m._push_clock()
+        m0.handle.check(self.lib.gb25_loop_all(self._hs, len(self.models), m0.clock.last_Δt, int(Ninner)))
+        for m in self.models:
+            m._pull_clock()
+
+    def synchronize(self): self._each(lambda m: m.synchronize())
+
+    def scatter_interior(self, name, a):
+        a = np.asarray(a)
+        for m in self.models:
+            Rx, Ry, rx, ry = m.partition
+            g = m.grid
+            sl = M._interior_slices(g, M.FIELD_LOC[name])
+            nyl = sl[1].stop - sl[1].start
+            m.set_interior(name, np.ascontiguousarray(a[:, ry * g.Ny: ry * g.Ny + nyl, rx * g.Nx:(rx + 1) * g.Nx]))
+
+    def gather_interior(self, name):
+        g = self.models[0].grid
+        rows = []
+        for y in range(self.Ry):
+            parts = [self.models[x + self.Rx * y].interior(name) for x in range(self.Rx)]
+            row = np.concatenate(parts, axis=2)
+            rows.append(row[:, :g.Ny] if y < self.Ry - 1 else row)
+        return np.concatenate(rows, axis=1)
+
+    def close(self):
+        self.synchronize()
+        self._each(lambda m: m.close())
+
+
 def partition_check(dist, local_rank, grid_type="gaussian_islands", tx=64, ty=48, Nz=10, nsteps=5, log=None):
     """The reference's sharded correctness protocol
     (/root/reference/correctness/correctness_sharded_baroclinic_instability_simulation_run.jl: a sharded model against

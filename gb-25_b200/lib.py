@@ -42,9 +42,11 @@ EXPORTED_SYMBOLS = (
     "gb25_initialize", "gb25_update_state", "gb25_first_time_step", "gb25_time_step", "gb25_loop",
     "gb25_synchronize", "gb25_mask_immersed_fields", "gb25_fill_halo_regions", "gb25_compute_auxiliaries",
     "gb25_compute_tendencies", "gb25_compute_momentum_tendencies", "gb25_compute_tracer_tendencies",
+    "gb25_compute_boundary_tendencies", "gb25_set_flux_boundary_condition",
     "gb25_ab2_step", "gb25_correct_velocities_and_cache_previous_tendencies",
     "gb25_last_loop_seconds", "gb25_kernel_launch_count", "gb25_enable_stage_timers", "gb25_get_stage_times",
     "gb25_exchange_blob_size", "gb25_exchange_export", "gb25_exchange_connect",
+    "gb25_exchange_connect_local", "gb25_loop_all",
 )
 
 
@@ -91,7 +93,7 @@ def load():
     for name in ("gb25_destroy", "gb25_clear_error", "gb25_initialize", "gb25_update_state", "gb25_synchronize",
                  "gb25_mask_immersed_fields", "gb25_fill_halo_regions", "gb25_compute_auxiliaries",
                  "gb25_compute_tendencies", "gb25_compute_momentum_tendencies", "gb25_compute_tracer_tendencies",
-                 "gb25_correct_velocities_and_cache_previous_tendencies"):
+                 "gb25_compute_boundary_tendencies", "gb25_correct_velocities_and_cache_previous_tendencies"):
         getattr(lib, name).argtypes = [H]
     lib.gb25_field_shape.argtypes = [H, C.c_int, C.POINTER(C.c_int)]
     lib.gb25_set_field.argtypes = [H, C.c_int, C.c_void_p]
@@ -101,6 +103,7 @@ def load():
     lib.gb25_get_interior.argtypes = [H, C.c_int, C.c_void_p]
     lib.gb25_set_fields.argtypes = [H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_int]
     lib.gb25_get_fields.argtypes = [H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.c_int]
+    lib.gb25_set_flux_boundary_condition.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
     lib.gb25_set_clock.argtypes = [H, C.c_double, C.c_long, C.c_float]
     lib.gb25_get_clock.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_long), C.POINTER(C.c_float)]
     lib.gb25_first_time_step.argtypes = [H, C.c_float]
@@ -114,6 +117,8 @@ def load():
     lib.gb25_exchange_blob_size.restype = C.c_int
     lib.gb25_exchange_export.argtypes = [H, C.c_void_p]
     lib.gb25_exchange_connect.argtypes = [H, C.c_void_p, C.c_int]
+    lib.gb25_exchange_connect_local.argtypes = [C.POINTER(H), C.c_int]
+    lib.gb25_loop_all.argtypes = [C.POINTER(H), C.c_int, C.c_float, C.c_int]
     _lib = lib
     return lib
 
@@ -228,6 +233,19 @@ class Handle:
 
     def get_fields(self, names, arrays, interior=False):
         self._batch(self.lib.gb25_get_fields, names, arrays, interior)
+
+    def set_flux_boundary_condition(self, name, side, values):
+        """FluxBoundaryCondition(values) at the "bottom" / "top" of u, v, T or S; None = default no-flux."""
+        sd = ("bottom", "top").index(side)
+        if values is None:
+            self.check(self.lib.gb25_set_flux_boundary_condition(self.h, FIELD_ID[name], sd, None))
+            return
+        two_d = {"u": "U", "v": "V", "T": "eta", "S": "eta"}[name]
+        shp = self.field_shape(two_d)[1:]
+        a = _f32(values)
+        if a.shape != shp:
+            raise ValueError(f"flux of {name}: need a 2-D parent of shape {shp}, got {a.shape}")
+        self.check(self.lib.gb25_set_flux_boundary_condition(self.h, FIELD_ID[name], sd, a.ctypes.data))
 
     def set_clock(self, time, iteration, last_dt):
         self.check(self.lib.gb25_set_clock(self.h, time, iteration, last_dt))

@@ -214,7 +214,17 @@ def correct_velocities_and_cache_previous_tendencies_workload(model, Δt=None):
 
 
 def compute_boundary_tendencies_workload(model):
-    """No-op: the benchmark model has default (no-flux) boundary conditions."""
+    """compute_boundary_tendencies_workload! (src/precompile.jl:52-61): adds the flux boundary conditions to Gⁿ.  The
+    benchmark model has default (no-flux) boundary conditions, for which this does nothing."""
+    _call(model, "gb25_compute_boundary_tendencies")
+
+
+def set_flux_boundary_condition(model, name, side, values):
+    """``FieldBoundaryConditions(top=FluxBoundaryCondition(values))`` of ``name`` ∈ (u, v, T, S), ``side`` ∈ ("bottom",
+    "top"): a 2-D parent-shaped array, or None for the default no-flux condition (how
+    src/data_free_ocean_climate_model.jl passes wind stress and surface heat / salt fluxes)."""
+    target = model.handle if hasattr(model.handle, "set_flux_boundary_condition") else model
+    target.set_flux_boundary_condition(name, side, values)
 
 
 def fill_halo_regions_workload(model):

@@ -146,6 +146,15 @@ int gb25_compute_auxiliaries(gb25_handle* h);        /* precompile.jl:113-115 (w
 int gb25_compute_tendencies(gb25_handle* h);         /* precompile.jl:48-50                                */
 int gb25_compute_momentum_tendencies(gb25_handle* h);/* precompile.jl:63-73                                */
 int gb25_compute_tracer_tendencies(gb25_handle* h);  /* precompile.jl:75-111                               */
+int gb25_compute_boundary_tendencies(gb25_handle* h);/* precompile.jl:52-61  (flux boundary conditions)    */
+/* FluxBoundaryCondition at the bottom (side 0) or top (side 1) of u, v, T or S (field = GB25_U / GB25_V / GB25_T /
+ * GB25_S): a 2-D parent-shaped host array ((Nx+2Hx) x (Ny+2Hy[+1]), x fastest) of fluxes in the units of the field times
+ * m/s, or NULL for the default no-flux condition.  What the `boundary_conditions` keyword of the model constructor fixes
+ * (src/data_free_ocean_climate_model.jl:12-70 builds wind stress and heat / salt fluxes this way); the benchmark model of
+ * src/baroclinic_instability_model.jl has none, and gb25_compute_boundary_tendencies is then a no-op.  With a flux set,
+ * gb25_compute_tendencies / gb25_update_state / the step entry points add G[i,j,1] += J_bottom Az / V and
+ * G[i,j,Nz] -= J_top Az / V after the interior tendencies, as Oceananigans' apply_z_bcs! does. */
+int gb25_set_flux_boundary_condition(gb25_handle* h, int field, int side, const float* flux_parent_2d);
 int gb25_ab2_step(gb25_handle* h, float dt, float chi); /* precompile.jl:121-123 (incl. split-explicit)    */
 int gb25_correct_velocities_and_cache_previous_tendencies(gb25_handle* h); /* precompile.jl:125-127         */
 
@@ -165,6 +174,14 @@ int gb25_get_stage_times(gb25_handle* h, const char** names, float* ms, long* ca
 int gb25_exchange_blob_size(void);
 int gb25_exchange_export(gb25_handle* h, void* blob);
 int gb25_exchange_connect(gb25_handle* h, const void* blobs, int nranks);
+/* Multi-GPU, ONE process driving all devices of the node — the reference's configuration
+ * (sharding/sharded_baroclinic_instability_simulation_run.jl:49, single_gpu_per_process=false): handles[r] is the tile of rank
+ * r = rx + Rx*ry, each created on its own device (gb25_config.device).  Peer access is enabled between the devices and the
+ * neighbours' allocations are used directly (no IPC).  gb25_loop_all enqueues every step on every tile in turn; per-tile
+ * calls (gb25_time_step, gb25_first_time_step, ...) must likewise be issued for all tiles before any of them is
+ * synchronised. */
+int gb25_exchange_connect_local(gb25_handle** handles, int n);
+int gb25_loop_all(gb25_handle** handles, int n, float dt, int nsteps);
 
 #ifdef __cplusplus
 }

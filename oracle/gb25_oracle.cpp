@@ -75,6 +75,7 @@ struct Oracle {
   std::vector<FT> Hcc, Hfc, Hcf;
   std::vector<FT> wts;
   std::vector<FT> fld[F_COUNT];
+  std::vector<FT> bflux[4][2];   // A7: flux boundary conditions of u, v, T, S at the bottom (0) / top (1); empty = no-flux
   double time = 0;
   long iteration = 0;
   FT last_dt = 0;
@@ -649,6 +650,26 @@ struct Oracle {
       }
     }
   }
+  // ------------------------------------------------- boundary tendency contributions (row A7)
+  // compute_hydrostatic_boundary_tendency_contributions! -> apply_z_bcs! [OCN-recall: BoundaryConditions/apply_flux_bcs.jl]:
+  //   Gc[i,j,1]  += J_bottom * Az / V(i,j,1),   Gc[i,j,Nz] -= J_top * Az / V(i,j,Nz)      (a positive top flux leaves the domain)
+  // with Az and V at the location of the field.  Reference call site: /root/reference/src/precompile.jl:52-61.
+  void boundary_tendencies() {
+    const int fg[4] = {F_GNU, F_GNV, F_GNT, F_GNS};
+    const std::vector<FT>* az[4] = {&azfc, &azcf, &azcc, &azcc};
+    for (int q = 0; q < 4; q++)
+      for (int side = 0; side < 2; side++) {
+        if (bflux[q][side].empty()) continue;
+        const int k = side ? Nz : 1;
+#pragma omp parallel for
+        for (int j = 1; j <= Ny; j++)
+          for (int i = 1; i <= Nx; i++) {
+            const FT A = (*az[q])[id2(i, j)], V = A * Dzc(k);
+            const FT d = bflux[q][side][id2(i, j)] * A / V;
+            if (side) at(fg[q], i, j, k) -= d; else at(fg[q], i, j, k) += d;
+          }
+      }
+  }
   void compute_tendencies() {
     momentum_tendency();
     tracer_tendency(F_T, F_GNT);
@@ -659,6 +680,7 @@ struct Oracle {
       vertical_diffusion_explicit(F_T, F_GNT, {0, 0, 0}, (FT)c.kappa);
       vertical_diffusion_explicit(F_S, F_GNS, {0, 0, 0}, (FT)c.kappa);
     }
+    boundary_tendencies();
   }
   void compute_auxiliaries() { compute_w(); compute_p(); }
   void update_state() {
@@ -837,8 +859,14 @@ struct Oracle {
       case 11: o->compute_p(); break;                                                                        \
       case 12: o->momentum_tendency(); break;                                                                \
       case 13: o->tracer_tendency(F_T, F_GNT); o->tracer_tendency(F_S, F_GNS); break;                        \
+      case 14: o->boundary_tendencies(); break;                                                              \
       default: break;                                                                                        \
     }                                                                                                        \
+  }                                                                                                          \
+  extern "C" void gb25o_set_flux_bc_##SUF(void* h, int q, int side, const FT* a) {                          \
+    Oracle<FT>* o = (Oracle<FT>*)h;                                                                          \
+    if (q < 0 || q > 3 || side < 0 || side > 1) return;                                                      \
+    if (a) o->bflux[q][side].assign(a, a + o->n2); else o->bflux[q][side].clear();                           \
   }                                                                                                          \
   extern "C" void gb25o_fill_halo_##SUF(void* h, int f, int lx, int ly, int lz, double sign, int three_d) {  \
     ((Oracle<FT>*)h)->fill_halo(f, Loc{lx, ly, lz}, (FT)sign, three_d != 0);                                 \

@@ -72,6 +72,7 @@ def load():
             getattr(_lib, f"gb25o_set_clock_{suf}").argtypes = [C.c_void_p, C.c_double, C.c_long, C.c_double]
             getattr(_lib, f"gb25o_op_{suf}").argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
             getattr(_lib, f"gb25o_fill_halo_{suf}").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
+            getattr(_lib, f"gb25o_set_flux_bc_{suf}").argtypes = [C.c_void_p, C.c_int, C.c_int, P]
             getattr(_lib, f"gb25o_rho_prime_{suf}").restype = ft
             getattr(_lib, f"gb25o_rho_prime_{suf}").argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
             getattr(_lib, f"gb25o_weno_{suf}").restype = ft
@@ -85,6 +86,7 @@ _OPS = {
     "gb25_compute_tendencies": 7, "gb25_ab2_step": 8,
     "gb25_correct_velocities_and_cache_previous_tendencies": 9,
     "gb25_compute_momentum_tendencies": 12, "gb25_compute_tracer_tendencies": 13,
+    "gb25_compute_boundary_tendencies": 14,
 }
 
 
@@ -188,6 +190,19 @@ class OracleModel(ModelBase):
         if a.shape != s:
             raise ValueError(f"{name}: parent shape {a.shape} != {s}")
         self.raw(name)[:s[0], :s[1], :s[2]] = a.astype(self.dtype)
+
+    def set_flux_boundary_condition(self, name, side, values):
+        """FluxBoundaryCondition(values) at the bottom / top of u, v, T or S; None = default no-flux."""
+        g = self.grid
+        q, sd = ("u", "v", "T", "S").index(name), ("bottom", "top").index(side)
+        fn = getattr(self.lib, f"gb25o_set_flux_bc_{self.suf}")
+        if values is None:
+            fn(self.h, q, sd, None)
+            return
+        a = np.zeros((g.PY, g.PX), dtype=self.dtype)
+        v = np.asarray(values, dtype=np.float32).astype(self.dtype)
+        a[:v.shape[0], :v.shape[1]] = v
+        fn(self.h, q, sd, a.ctypes.data_as(C.POINTER(self.ft)))
 
     def kbot(self):
         g = self.grid

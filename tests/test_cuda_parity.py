@@ -426,6 +426,42 @@ def test_vertical_diffusion_closures(oracle_mod, grid_type, Nx, Ny, Nz, closure)
     assert dT > 1e-5 and du > 1e-2
 
 
+@pytest.mark.parametrize("grid_type,Nx,Ny,Nz", GRIDS)
+def test_flux_boundary_conditions(oracle_mod, grid_type, Nx, Ny, Nz):
+    """Row A7: compute_boundary_tendencies_workload! with flux boundary conditions (wind stress on u, v, a surface heat flux,
+    bottom fluxes on u and S) — the operator on identical inputs, then five steps, against the oracle."""
+    rm, vm = make_models(grid_type, Nx, Ny, Nz, 60.0, oracle_mod)
+    rng = np.random.default_rng(9)
+    for name, side, scale in (("u", "top", 1e-4), ("v", "top", 1e-4), ("T", "top", 1e-4), ("u", "bottom", 1e-5), ("S", "bottom", 1e-6)):
+        two_d = {"u": "U", "v": "V", "T": "eta", "S": "eta"}[name]
+        J = (scale * rng.standard_normal(rm.handle.field_shape(two_d)[1:])).astype(np.float32)
+        for m in (rm, vm):
+            M.set_flux_boundary_condition(m, name, side, J)
+    M.initialize(vm); M.update_state(vm)
+    for n in STATE_FIELDS:
+        rm.set_parent(n, vm.parent(n))
+    before = {n: vm.parent(n) for n in ("Gn_u", "Gn_v", "Gn_T", "Gn_S")}
+    M.compute_boundary_tendencies_workload(vm); M.compute_boundary_tendencies_workload(rm)
+    for n in before:
+        a, b = rm.parent(n), vm.parent(n)
+        assert np.abs(b - before[n]).max() > 0, n                                  # the operator did something
+        assert np.allclose(a, b, rtol=2e-6, atol=0), (n, float(np.abs(a - b).max()))
+    for m in (rm, vm):
+        M.first_time_step(m)
+        M.loop(m, 4)
+    _, v64 = make_models(grid_type, Nx, Ny, Nz, 60.0, oracle_mod, dtype=np.float64, with_cuda=False)
+    # the Float64 oracle with the same conditions is the truth for the "as close as the Float32 oracle" criterion
+    rng = np.random.default_rng(9)
+    for name, side, scale in (("u", "top", 1e-4), ("v", "top", 1e-4), ("T", "top", 1e-4), ("u", "bottom", 1e-5), ("S", "bottom", 1e-6)):
+        two_d = {"u": "U", "v": "V", "T": "eta", "S": "eta"}[name]
+        J = (scale * rng.standard_normal(rm.handle.field_shape(two_d)[1:])).astype(np.float32)
+        M.set_flux_boundary_condition(v64, name, side, J)
+    M.first_time_step(v64)
+    M.loop(v64, 4)
+    _assert_as_close_as_f32(rm, vm, v64, ("u", "v", "w", "T", "S", "eta", "Gn_u", "Gn_v", "Gn_T", "Gn_S"))
+    rm.close()
+
+
 def test_baseline_config_c1_latlon_128x64x8_100_steps(oracle_mod):
     """BASELINE.json configs[0]: baroclinic_instability_model on LatitudeLongitudeGrid 128x64x8, Float32,
     1 Euler + 100 AB2 steps, reference state (T = S = 0, random u, v), against the oracle."""

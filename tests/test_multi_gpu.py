@@ -27,3 +27,41 @@ def test_partitioned_run_is_bit_identical_to_single_gpu(grid_type, world):
            grid_type, "64", "48", "10", "5"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "DIST_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("grid_type", ["simple_lat_lon", "gaussian_islands"])
+def test_single_process_drives_two_devices(grid_type):
+    """The reference drives all GPUs of a node from ONE process (sharded_..._run.jl:49): two handles on two devices, connected
+    with gb25_exchange_connect_local (peer access, no IPC), stepped through the C ABI from this process — bit-identical to the
+    single-GPU run of the same global problem."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import numpy as np
+    import gb25_b200  # noqa: F401
+    from gb25_b200 import distributed as D, grids, model as M
+    tx, ty, Nz = 64, 48, 10
+    P = D.LocalPartition(tx, ty, Nz, Δt=60.0, grid_type=grid_type, devices=(0, 1))
+    gg = P.global_grid
+    rng = np.random.default_rng(42)
+    T, S = grids.baroclinic_instability_state(gg)
+    ny_v = gg.Ny + (1 if gg.topo_y == grids.TOPO_BOUNDED else 0)
+    state = {"T": T.astype(np.float32), "S": S.astype(np.float32),
+             "u": (1e-3 * rng.random((Nz, gg.Ny, gg.Nx))).astype(np.float32),
+             "v": (1e-3 * rng.random((Nz, ny_v, gg.Nx))).astype(np.float32)}
+    for n, a in state.items():
+        P.scatter_interior(n, a)
+    P.synchronize()
+    P.first_time_step()
+    P.time_step()
+    P.loop(4)
+    P.synchronize()
+    ref = M.baroclinic_instability_model(M.B200(0), gg.Nx, gg.Ny, Nz, Δt=60.0, grid_type=grid_type)
+    for n, a in state.items():
+        ref.set_interior(n, a)
+    M.first_time_step(ref); M.time_step(ref); M.loop(ref, 4)
+    assert P.models[0].clock.iteration == ref.clock.iteration == 6
+    for n in ("u", "v", "w", "T", "S", "eta", "Gn_u", "Gn_T", "U", "filt_U"):
+        r, g = ref.interior(n), P.gather_interior(n)
+        g = g[:, :r.shape[1]]
+        assert np.array_equal(r[:, :g.shape[1]].view(np.uint32), g.view(np.uint32)), n
+    P.close(); ref.close()

@@ -288,3 +288,29 @@ def test_vertical_diffusion_known_answers(oracle_mod):
         mu = dt * K * (4.0 / dz ** 2) * np.sin(np.pi * mm / 24) ** 2
         assert np.allclose(amp, 1.0 / (1.0 + mu) if cl == 2 else 1.0 - mu, rtol=1e-9)          # (iii)
     assert np.abs(out[1] - out[2]).max() < 2.0 * mu ** 2   # (i)
+
+
+def test_flux_boundary_conditions_known_answer(oracle_mod):
+    """Row A7 (apply_z_bcs!): at rest, a top flux J on T gives Gⁿ.T[i,j,Nz] = -J/Δz(Nz) and nothing else; a bottom flux on u
+    gives Gⁿ.u[i,j,1] = +J/Δz(1); clearing the condition restores the no-flux tendencies."""
+    from gb25_b200 import model as M
+    m = M.baroclinic_instability_model(oracle_mod.CPUOracle(np.float64), 32, 16, 6, Δt=60.0, grid_type="simple_lat_lon",
+                                       model_cls=oracle_mod.OracleModel)
+    g = m.grid
+    rng = np.random.default_rng(0)
+    JT = rng.standard_normal((g.PY, g.PX)).astype(np.float32)
+    Ju = rng.standard_normal((g.PY, g.PX)).astype(np.float32)
+    M.set_flux_boundary_condition(m, "T", "top", JT)
+    M.set_flux_boundary_condition(m, "u", "bottom", Ju)
+    M.update_state(m)
+    dz = np.asarray(g.z["dz_c"], dtype=np.float32).astype(np.float64)      # the model holds Float32 grid products
+    GT, Gu = m.interior("Gn_T"), m.interior("Gn_u")
+    inner = (slice(g.Hy, g.Hy + g.Ny), slice(g.Hx, g.Hx + g.Nx))
+    assert np.allclose(GT[-1], -JT[inner].astype(np.float64) / dz[g.Hz + g.Nz - 1], rtol=1e-12, atol=0)
+    assert not GT[:-1].any()
+    assert np.allclose(Gu[0], Ju[inner].astype(np.float64) / dz[g.Hz], rtol=1e-12, atol=0)
+    assert not Gu[1:].any() and not m.interior("Gn_v").any()
+    M.set_flux_boundary_condition(m, "T", "top", None)
+    M.set_flux_boundary_condition(m, "u", "bottom", None)
+    M.update_state(m)
+    assert not m.interior("Gn_T").any() and not m.interior("Gn_u").any()
