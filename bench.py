@@ -256,6 +256,9 @@ def main():
                     help="N > 1: weak = the workload's tile on every GPU (default); strong = the workload's GLOBAL grid "
                          "split over (Rx, Ry) = factors(N) (BASELINE.json configs[2])")
     ap.add_argument("--no-partition-check", action="store_true")
+    ap.add_argument("--float-type", default="Float32", choices=["Float32", "Float64"],
+                    help="Float32 = BASELINE.json's metric (default); Float64 = libgb25cuda_f64.so, reported beside the "
+                         "reference's published Float64 numbers (BASELINE.md)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args, args.workload)
@@ -296,12 +299,13 @@ def main():
                                               log=(lambda m: print(m, file=sys.stderr)) if rank == 0 else None)
                             for gt in ("simple_lat_lon", "gaussian_islands"))
 
+    FT = np.float64 if args.float_type == "Float64" else np.float32
     if world > 1:
         from gb25_b200 import distributed as D
         model = D.sharded_baroclinic_instability_model(M.B200(local_rank), Nx, Ny, Nz, Δt=dt, grid_type=grid_type,
-                                                       Rx=Rx, Ry=Ry, rank=rank, dist=dist)
+                                                       Rx=Rx, Ry=Ry, rank=rank, dist=dist, float_type=FT)
     else:
-        model = M.baroclinic_instability_model(M.B200(local_rank), Nx, Ny, Nz, Δt=dt, grid_type=grid_type)
+        model = M.baroclinic_instability_model(M.B200(local_rank), Nx, Ny, Nz, Δt=dt, grid_type=grid_type, float_type=FT)
     synthetic_state(model, seed=42 + rank)
     if dist is not None:
         from gb25_b200 import distributed as D
@@ -352,7 +356,7 @@ def main():
         names = ("u", "v", "T", "S", "eta", "U", "V")
         host = []
         for n in names:
-            tns = torch.empty(model.handle.interior_shape(n), dtype=torch.float32, pin_memory=True)
+            tns = torch.empty(model.handle.interior_shape(n), dtype=torch.float64 if FT is np.float64 else torch.float32, pin_memory=True)
             host.append(tns.numpy())
         model.handle.get_fields(names, host, interior=True)
         nb = sum(a.nbytes for a in host)
@@ -379,7 +383,8 @@ def main():
         # the reference's own usage (sync_states!, loop!(model, Ninner), compare_states): one upload, Ninner steps in one
         # host call, one download — reported beside the per-step protocol, not instead of it
         ninner = args.steps
-        phost = [torch.empty(model.handle.field_shape(n), dtype=torch.float32, pin_memory=True).numpy() for n in names]
+        phost = [torch.empty(model.handle.field_shape(n), dtype=torch.float64 if FT is np.float64 else torch.float32,
+                             pin_memory=True).numpy() for n in names]
         model.handle.get_fields(names, phost)
         pb = sum(a.nbytes for a in phost)
         barrier()
@@ -439,7 +444,7 @@ def main():
     line = {"metric": "cell_steps_per_s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64" if FT is np.float64 else "f32", "data": "synthetic",
             "config": {"workload": args.workload, "grid": grid_type, "Nx_per_gpu": Nx, "Ny_per_gpu": Ny, "Nz": Nz, "dt": dt,
                        "partition": [Rx, Ry], "halo": 8, "substeps": 30, "l2": "inputs larger than L2 (each 3-D field is 226 MB)"
                        if Nx * Ny * Nz * 4 > 126e6 else "working set fits in L2: latency-bound config",

@@ -2,8 +2,9 @@
 
 ``parse_baroclinic_instability_args`` (arg_parsing.jl:9-47) returns a dict with the reference's keys ("grid-x", "grid-y",
 "grid-z", "float-type", "target-float-type", "limbs", "dimension"); ``float_type_from_args`` (:75-77) maps the string to a
-type.  libgb25cuda computes in Float32 (the Float64 build is SURVEY section 8 row f-4), so ``require_float32`` is what the
-run scripts call before building a model; the multifloat lowering (:96-104) is a Reactant feature and has no counterpart."""
+type.  libgb25cuda is built for Float32 (libgb25cuda.so, all kernel generations) and Float64 (libgb25cuda_f64.so, the
+operator-per-kernel generation): ``supported_float_type`` is what the run scripts call before building a model; the
+multifloat lowering (:96-104) is a Reactant feature and has no counterpart."""
 from __future__ import annotations
 
 import argparse
@@ -61,10 +62,10 @@ def multifloat_from_args(parsed_args: dict):
     raise NotImplementedError("multifloat lowering (Reactant.MultiFloatOptions) has no counterpart in libgb25cuda")
 
 
-def require_float32(parsed_args: dict):
-    """The library's arithmetic type; anything else is refused loudly instead of being silently down-cast."""
+def supported_float_type(parsed_args: dict):
+    """Float32 or Float64 (the two builds of the library); anything else is refused loudly instead of being silently cast."""
     t = float_type_from_args(parsed_args)
-    if t is not np.float32:
-        raise ValueError(f"libgb25cuda computes in Float32; --float-type {parsed_args['float-type']} is not built "
-                         "(pass --float-type Float32; the Float64 build is listed as next in DESIGN.md)")
+    if t is not np.float32 and t is not np.float64:
+        raise ValueError(f"libgb25cuda is built for Float32 and Float64; --float-type {parsed_args['float-type']} is not "
+                         "available")
     return t

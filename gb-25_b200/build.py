@@ -56,6 +56,38 @@ def build_variant(suffix, defines, verbose=False):
     return lib
 
 
+F64_SOURCES = ["gb25_api.cu", "gb25_kernels.cu", "gb25_exchange.cu", "gb25_f64_stubs.cu"]
+LIB_F64 = os.path.join(CSRC, "libgb25cuda_f64.so")
+
+
+def build_f64(force=False, verbose=False):
+    """libgb25cuda_f64.so: the same sources with -DGB25_F64 (scalar type double), operator-per-kernel generation only."""
+    srcs = [os.path.join(CSRC, s) for s in F64_SOURCES]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    deps.append(os.path.join(ROOT, "include", "gb25cuda.h"))
+    if not force and not _newer(LIB_F64, deps):
+        return LIB_F64
+    nvcc = _nvcc()
+    odir = os.path.join(CSRC, "build", "f64")
+    os.makedirs(odir, exist_ok=True)
+    objs, procs = [], []
+    for s in srcs:
+        o = os.path.join(odir, os.path.basename(s)[:-3] + ".o")
+        objs.append(o)
+        cmd = [nvcc, *[f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")], "-DGB25_F64", "-c", s, "-o", o]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    subprocess.check_call([nvcc, "-shared", "-o", LIB_F64, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    return LIB_F64
+
+
 def build_cuda(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s))]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
@@ -89,3 +121,4 @@ if __name__ == "__main__":
         print(build_variant(sys.argv[q + 1], [a for a in sys.argv[q + 2:] if a.startswith("-D")], verbose="-v" in sys.argv))
     else:
         print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))
+        print(build_f64(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -82,6 +82,7 @@ static int upload(Handle* h, const T* host, size_t n, const T** out) {
 }
 
 extern "C" int gb25_abi_version(void) { return GB25_ABI_VERSION; }
+extern "C" int gb25_real_bytes(void) { return (int)sizeof(real); }
 
 extern "C" const char* gb25_last_error(const gb25_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 extern "C" int gb25_clear_error(gb25_handle* h) {
@@ -99,14 +100,14 @@ static int build_immersed_products(Handle* h, const gb25_grid* grid) {
   auto zc = [&](int k) { return grid->z_c[k + c.Hz - 1]; };
   (void)PZ;
   std::vector<short> kb(n2, 0), kbe(n2, 0);
-  std::vector<float> Hcc(n2), Hfc(n2), Hcf(n2);
-  const float ztop = zf(c.Nz + 1), zbot = zf(1);
+  std::vector<real> Hcc(n2), Hfc(n2), Hcf(n2);
+  const real ztop = zf(c.Nz + 1), zbot = zf(1);
   for (int J = 0; J < PY; J++)
     for (int I = 0; I < PX; I++) {
       const int q = I + PX * J;
       int k0 = 0;
       if (c.immersed && grid->bottom_height) {
-        const float bh = std::min(std::max(grid->bottom_height[q], zbot), ztop);
+        const real bh = std::min(std::max(grid->bottom_height[q], zbot), ztop);
         for (int k = 1; k <= c.Nz; k++) if (zc(k) <= bh) k0 = k;
       }
       kb[q] = (short)k0;
@@ -271,15 +272,15 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
   g.wall_n = (cfg->ry == cfg->Ry - 1) && (cfg->topo_y == GB25_TOPO_BOUNDED);
   h->cfg.immersed = g.immersed;
   const size_t n2 = g.n2, n3 = n2 * g.PZ;
-  const float* src2[13] = {grid->dx_cc, grid->dx_fc, grid->dx_cf, grid->dx_ff, grid->dy_cc, grid->dy_fc, grid->dy_cf, grid->dy_ff,
+  const real* src2[13] = {grid->dx_cc, grid->dx_fc, grid->dx_cf, grid->dx_ff, grid->dy_cc, grid->dy_fc, grid->dy_cf, grid->dy_ff,
                            grid->az_cc, grid->az_fc, grid->az_cf, grid->az_ff, grid->f_ff};
-  const float** dst2[13] = {&g.dxcc, &g.dxfc, &g.dxcf, &g.dxff, &g.dycc, &g.dyfc, &g.dycf, &g.dyff, &g.azcc, &g.azfc, &g.azcf, &g.azff, &g.fff};
+  const real** dst2[13] = {&g.dxcc, &g.dxfc, &g.dxcf, &g.dxff, &g.dycc, &g.dyfc, &g.dycf, &g.dyff, &g.azcc, &g.azfc, &g.azcf, &g.azff, &g.fff};
   for (int a = 0; a < 13; a++) {
     if (!src2[a]) { g_create_error = "gb25_create: missing metric array"; gb25_destroy(h); return GB25_ERR_INVALID; }
     CKC(upload(h, src2[a], n2, dst2[a]));
   }
-  const float* srcz[4] = {grid->z_f, grid->z_c, grid->dz_c, grid->dz_f};
-  const float** dstz[4] = {&g.zf, &g.zc, &g.dzc, &g.dzf};
+  const real* srcz[4] = {grid->z_f, grid->z_c, grid->dz_c, grid->dz_f};
+  const real** dstz[4] = {&g.zf, &g.zc, &g.dzc, &g.dzf};
   for (int a = 0; a < 4; a++) CKC(upload(h, srcz[a], (size_t)g.PZ, dstz[a]));
   CKC(build_immersed_products(h, grid));
   {
@@ -291,37 +292,40 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
   // fields
   for (int fidx = 0; fidx < GB25_FIELD_COUNT; fidx++) {
     const size_t n = kFieldInfo[fidx].three_d ? n3 : n2;
-    float* d = nullptr;
-    cudaError_t ce = cudaMalloc(&d, n * sizeof(float));
+    real* d = nullptr;
+    cudaError_t ce = cudaMalloc(&d, n * sizeof(real));
     if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc field: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
     h->allocs.push_back(d);
-    CKC(ckcuda(cudaMemsetAsync(d, 0, n * sizeof(float), h->stream), "cudaMemset"));
+    CKC(ckcuda(cudaMemsetAsync(d, 0, n * sizeof(real), h->stream), "cudaMemset"));
     h->field_ptr[fidx] = d;
   }
   for (int q = 0; q < 4; q++) {
     static const int ids[4] = {GB25_U, GB25_V, GB25_T, GB25_S};
     h->state_buf[0][q] = h->field_ptr[ids[q]];
-    cudaError_t ce = cudaMalloc(&h->state_buf[1][q], n3 * sizeof(float));
+    cudaError_t ce = cudaMalloc(&h->state_buf[1][q], n3 * sizeof(real));
     if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc state buffer: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
     h->allocs.push_back(h->state_buf[1][q]);
-    CKC(ckcuda(cudaMemsetAsync(h->state_buf[1][q], 0, n3 * sizeof(float), h->stream), "cudaMemset"));
+    CKC(ckcuda(cudaMemsetAsync(h->state_buf[1][q], 0, n3 * sizeof(real), h->stream), "cudaMemset"));
   }
-  for (float** sp : {&h->zeta, &h->dxU, &h->dyV}) {
-    cudaError_t ce = cudaMalloc(sp, n3 * sizeof(float));
+  for (real** sp : {&h->zeta, &h->dxU, &h->dyV}) {
+    cudaError_t ce = cudaMalloc(sp, n3 * sizeof(real));
     if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc scratch: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
     h->allocs.push_back(*sp);
-    CKC(ckcuda(cudaMemsetAsync(*sp, 0, n3 * sizeof(float), h->stream), "cudaMemset"));
+    CKC(ckcuda(cudaMemsetAsync(*sp, 0, n3 * sizeof(real), h->stream), "cudaMemset"));
   }
-  for (float** sp : {&h->us2, &h->vs2, &h->corr_u, &h->corr_v, &h->carry[0], &h->carry[1], &h->carry[2], &h->carry[3],
+  for (real** sp : {&h->us2, &h->vs2, &h->corr_u, &h->corr_v, &h->carry[0], &h->carry[1], &h->carry[2], &h->carry[3],
                      &h->spec2d[0], &h->spec2d[1], &h->spec2d[2], &h->spec2d[3]}) {
-    cudaError_t ce = cudaMalloc(sp, n2 * sizeof(float));
+    cudaError_t ce = cudaMalloc(sp, n2 * sizeof(real));
     if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc scratch: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
     h->allocs.push_back(*sp);
-    CKC(ckcuda(cudaMemsetAsync(*sp, 0, n2 * sizeof(float), h->stream), "cudaMemset"));
+    CKC(ckcuda(cudaMemsetAsync(*sp, 0, n2 * sizeof(real), h->stream), "cudaMemset"));
   }
   {
     const char* e = getenv("GB25_FUSED");
     h->use_fused = !(e && e[0] == '0');
+#ifdef GB25_F64
+    h->use_fused = false;     // Float64 build: the operator-per-kernel generation only
+#endif
     const char* t = getenv("GB25_TMA");
     h->use_tma = !(t && t[0] == '0');
     const char* sp = getenv("GB25_SPECULATE");
@@ -368,17 +372,17 @@ extern "C" int gb25_interior_shape(const gb25_handle* h, int field, int shape[3]
   return GB25_OK;
 }
 // one pitched 3-D copy between a host array (parent or interior shape) and the internal (PX, PY, PZ) layout
-static int copy_field(Handle* h, int field, float* host, bool to_device, bool interior = false, bool sync = true) {
+static int copy_field(Handle* h, int field, real* host, bool to_device, bool interior = false, bool sync = true) {
   if (field < 0 || field >= GB25_FIELD_COUNT || !host) { h->err = "bad field id or null buffer"; return GB25_ERR_INVALID; }
   int s[3];
   if (interior) interior_shape(h, field, s); else parent_shape(h, field, s);
   const DevGrid& g = h->g;
   const bool three_d = kFieldInfo[field].three_d;
   cudaMemcpy3DParms p = {};
-  p.extent = make_cudaExtent((size_t)s[0] * sizeof(float), s[1], s[2]);
-  cudaPitchedPtr hp = make_cudaPitchedPtr(host, (size_t)s[0] * sizeof(float), s[0], s[1]);
-  cudaPitchedPtr dp = make_cudaPitchedPtr(h->field_ptr[field], (size_t)g.PX * sizeof(float), g.PX, g.PY);
-  const cudaPos dpos = interior ? make_cudaPos((size_t)g.Hx * sizeof(float), g.Hy, three_d ? g.Hz : 0) : make_cudaPos(0, 0, 0);
+  p.extent = make_cudaExtent((size_t)s[0] * sizeof(real), s[1], s[2]);
+  cudaPitchedPtr hp = make_cudaPitchedPtr(host, (size_t)s[0] * sizeof(real), s[0], s[1]);
+  cudaPitchedPtr dp = make_cudaPitchedPtr(h->field_ptr[field], (size_t)g.PX * sizeof(real), g.PX, g.PY);
+  const cudaPos dpos = interior ? make_cudaPos((size_t)g.Hx * sizeof(real), g.Hy, three_d ? g.Hz : 0) : make_cudaPos(0, 0, 0);
   if (to_device) { p.srcPtr = hp; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
   else { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.kind = cudaMemcpyDeviceToHost; }
   CK(h, cudaMemcpy3DAsync(&p, h->stream));
@@ -390,40 +394,40 @@ static int copy_field(Handle* h, int field, float* host, bool to_device, bool in
     if (!interior)
       for (int q = 0; q < 4; q++)
         if (h->field_ptr[field] == h->state_buf[h->parity][q]) {
-          p.dstPtr = make_cudaPitchedPtr(h->state_buf[1 - h->parity][q], (size_t)g.PX * sizeof(float), g.PX, g.PY);
+          p.dstPtr = make_cudaPitchedPtr(h->state_buf[1 - h->parity][q], (size_t)g.PX * sizeof(real), g.PX, g.PY);
           CK(h, cudaMemcpy3DAsync(&p, h->stream));
         }
   }
   if (sync) CK(h, cudaStreamSynchronize(h->stream));
   return GB25_OK;
 }
-extern "C" int gb25_set_field(gb25_handle* h, int field, const float* host_parent) {
+extern "C" int gb25_set_field(gb25_handle* h, int field, const real* host_parent) {
   REQUIRE(h);
-  return copy_field(h, field, const_cast<float*>(host_parent), true);
+  return copy_field(h, field, const_cast<real*>(host_parent), true);
 }
-extern "C" int gb25_get_field(gb25_handle* h, int field, float* host_parent) {
+extern "C" int gb25_get_field(gb25_handle* h, int field, real* host_parent) {
   REQUIRE(h);
   return copy_field(h, field, host_parent, false);
 }
-extern "C" int gb25_set_interior(gb25_handle* h, int field, const float* host_interior) {
+extern "C" int gb25_set_interior(gb25_handle* h, int field, const real* host_interior) {
   REQUIRE(h);
-  return copy_field(h, field, const_cast<float*>(host_interior), true, true);
+  return copy_field(h, field, const_cast<real*>(host_interior), true, true);
 }
-extern "C" int gb25_get_interior(gb25_handle* h, int field, float* host_interior) {
+extern "C" int gb25_get_interior(gb25_handle* h, int field, real* host_interior) {
   REQUIRE(h);
   return copy_field(h, field, host_interior, false, true);
 }
-extern "C" int gb25_set_fields(gb25_handle* h, int n, const int* fields, const float* const* host, int interior) {
+extern "C" int gb25_set_fields(gb25_handle* h, int n, const int* fields, const real* const* host, int interior) {
   REQUIRE(h);
   if (n < 0 || (n && (!fields || !host))) { h->err = "gb25_set_fields: null argument"; return GB25_ERR_INVALID; }
   for (int q = 0; q < n; q++) {
-    const int rc = copy_field(h, fields[q], const_cast<float*>(host[q]), true, interior != 0, false);
+    const int rc = copy_field(h, fields[q], const_cast<real*>(host[q]), true, interior != 0, false);
     if (rc != GB25_OK) return rc;
   }
   CK(h, cudaStreamSynchronize(h->stream));     // the host buffers are borrowed for the duration of the call only
   return GB25_OK;
 }
-extern "C" int gb25_get_fields(gb25_handle* h, int n, const int* fields, float* const* host, int interior) {
+extern "C" int gb25_get_fields(gb25_handle* h, int n, const int* fields, real* const* host, int interior) {
   REQUIRE(h);
   if (n < 0 || (n && (!fields || !host))) { h->err = "gb25_get_fields: null argument"; return GB25_ERR_INVALID; }
   for (int q = 0; q < n; q++) {
@@ -617,7 +621,7 @@ extern "C" int gb25_compute_boundary_tendencies(gb25_handle* h) {
   { StageScope t(h, "boundary_tendencies"); launch_boundary_tendencies(h); }
   return check_async(h, "gb25_compute_boundary_tendencies");
 }
-extern "C" int gb25_set_flux_boundary_condition(gb25_handle* h, int field, int side, const float* flux) {
+extern "C" int gb25_set_flux_boundary_condition(gb25_handle* h, int field, int side, const real* flux) {
   REQUIRE(h);
   int q = -1;
   if (field == GB25_U) q = 0; else if (field == GB25_V) q = 1; else if (field == GB25_T) q = 2; else if (field == GB25_S) q = 3;
@@ -629,11 +633,11 @@ extern "C" int gb25_set_flux_boundary_condition(gb25_handle* h, int field, int s
   } else {
     int s[3];
     parent_shape(h, field == GB25_V ? GB25_BARO_V : (field == GB25_U ? GB25_BARO_U : GB25_ETA), s);   // 2-D parent of that staggering
-    float* d = nullptr;
-    CK(h, cudaMalloc(&d, (size_t)h->g.n2 * sizeof(float)));
+    real* d = nullptr;
+    CK(h, cudaMalloc(&d, (size_t)h->g.n2 * sizeof(real)));
     h->allocs.push_back(d);
-    CK(h, cudaMemset(d, 0, (size_t)h->g.n2 * sizeof(float)));
-    CK(h, cudaMemcpy2D(d, (size_t)h->g.PX * sizeof(float), flux, (size_t)s[0] * sizeof(float), (size_t)s[0] * sizeof(float), s[1], cudaMemcpyHostToDevice));
+    CK(h, cudaMemset(d, 0, (size_t)h->g.n2 * sizeof(real)));
+    CK(h, cudaMemcpy2D(d, (size_t)h->g.PX * sizeof(real), flux, (size_t)s[0] * sizeof(real), (size_t)s[0] * sizeof(real), s[1], cudaMemcpyHostToDevice));
     h->bflux[q][side] = d;
   }
   h->has_bflux = false;

@@ -30,7 +30,7 @@ struct ExBlob {
 };
 
 // --------------------------------------------------------------------------------- device side
-struct PushField { const float* src; float* dst; int lx, ly, lz; float sign; int flat; };
+struct PushField { const real* src; real* dst; int lx, ly, lz; real sign; int flat; };
 struct PushBatch { PushField f[9]; int n; };
 
 // rows [srow, srow+nrows) of src -> rows [drow, ...) of dst; interior columns; planes [p0, p0+np)
@@ -60,7 +60,7 @@ __global__ void k_push_cols(DevGrid g, PushBatch pb, int scol, int dcol, int nco
 // line into the neighbour's column inbox; after the handshake the receiver scatters its inbox into its own halo columns
 // (a local copy).  The inbox has two halves, used alternately by sequence parity: a neighbour that runs ahead may already
 // push the strips of the NEXT fill while this tile has not unpacked the current one.
-__global__ void k_push_cols_packed(DevGrid g, PushBatch pb, int scol, int three_d, float* __restrict__ box) {
+__global__ void k_push_cols_packed(DevGrid g, PushBatch pb, int scol, int three_d, real* __restrict__ box) {
   const int c = threadIdx.x;                                  // 0 .. Hx-1
   const int J = blockIdx.x * blockDim.y + threadIdx.y;        // storage row
   if (c >= g.Hx || J >= g.PY) return;
@@ -70,7 +70,7 @@ __global__ void k_push_cols_packed(DevGrid g, PushBatch pb, int scol, int three_
   box[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * g.PY + J) * g.Hx + c] = pf.src[po + scol + c];
 }
 // blockIdx.z = 2 * field slot + direction (0: from the west tile -> columns [0, Hx), 1: from the east tile -> [Nx+Hx, PX))
-__global__ void k_unpack_cols(DevGrid g, PushBatch pb, int three_d, const float* __restrict__ box_w, const float* __restrict__ box_e) {
+__global__ void k_unpack_cols(DevGrid g, PushBatch pb, int three_d, const real* __restrict__ box_w, const real* __restrict__ box_e) {
   const int c = threadIdx.x;
   const int J = blockIdx.x * blockDim.y + threadIdx.y;
   if (c >= g.Hx || J >= g.PY) return;
@@ -78,7 +78,7 @@ __global__ void k_unpack_cols(DevGrid g, PushBatch pb, int three_d, const float*
   const PushField pf = pb.f[q];
   if (pf.flat) { if (blockIdx.y > 0) return; three_d = 0; }
   const size_t po = (three_d ? (size_t)g.n2 * blockIdx.y : 0) + (size_t)g.PX * J;
-  const float* box = dir ? box_e : box_w;
+  const real* box = dir ? box_e : box_w;
   pf.dst[po + (dir ? g.Nx + g.Hx : 0) + c] = box[(((size_t)q * gridDim.y + blockIdx.y) * g.PY + J) * g.Hx + c];
 }
 // tripolar fold: my top rows -> the partner's north halo rows, x-mirrored, sign-flipped for vectors.
@@ -92,9 +92,9 @@ __global__ void k_push_fold(DevGrid g, PushBatch pb, int three_d, int nrows, int
   const int nk = three_d ? g.Nz + pf.lz : 1;
   const int k = blockIdx.y + 1;
   if (k > nk) return;
-  int id; float sg = pf.sign;
+  int id; real sg = pf.sign;
   if (pf.lx == 0) { if (second) return; id = g.Nx - is + 1; }
-  else if (is == 1) { if (!second) return; id = 1; if (quirk_pos) sg = fabsf(sg); }
+  else if (is == 1) { if (!second) return; id = 1; if (quirk_pos) sg = rabs(sg); }
   else { if (second) return; id = g.Nx + 2 - is; }
   const size_t po = three_d ? (size_t)g.n2 * (k + g.Hz - 1) : 0;
   for (int m = 1; m <= nrows; m++) {
@@ -121,14 +121,14 @@ __global__ void k_wait(volatile int* flags, int mask, int val) {
 }
 
 // --------------------------------------------------------------------------------- host side
-void exchange_table(Handle* h, float* tab[EX_NF]) {
+void exchange_table(Handle* h, real* tab[EX_NF]) {
   const DevFields& f = h->f;
-  float* t[EX_NF] = {h->state_buf[0][0], h->state_buf[0][1], h->state_buf[0][2], h->state_buf[0][3], f.eta, f.bu, f.bv, f.gU, f.gV,
+  real* t[EX_NF] = {h->state_buf[0][0], h->state_buf[0][1], h->state_buf[0][2], h->state_buf[0][3], f.eta, f.bu, f.bv, f.gU, f.gV,
                      h->state_buf[1][0], h->state_buf[1][1], h->state_buf[1][2], h->state_buf[1][3], h->ex.xbox};
   for (int q = 0; q < EX_NF; q++) tab[q] = t[q];
 }
-static int ex_field_id(Handle* h, const float* a) {
-  float* tab[EX_NF];
+static int ex_field_id(Handle* h, const real* a) {
+  real* tab[EX_NF];
   exchange_table(h, tab);
   for (int q = 0; q < EX_NF; q++) if (q != EX_XBOX && tab[q] == a) return q;
   return -1;
@@ -246,7 +246,7 @@ void launch_fill_halo_dist(Handle* h, const HaloSpec* specs, int n, bool three_d
     dim3 bc(g.Hx, 32), gc((g.PY + 31) / 32, np, 0);
     X.seq++;
     X.xseq++;     // (the parity of the column phases, not of all phases: a fill with a row phase advances seq twice)
-    float* const mybox = X.xbox + (size_t)(X.xseq & 1) * 2 * X.xbox_stride;
+    real* const mybox = X.xbox + (size_t)(X.xseq & 1) * 2 * X.xbox_stride;
     {
       StageScope ts(h, "exchange:push_x");
       const size_t off = (size_t)(X.xseq & 1) * 2 * X.xbox_stride;
@@ -312,8 +312,8 @@ static int exchange_alloc_windows(Handle* h) {
   }
   if (!X.xbox) {
     X.xbox_stride = (size_t)9 * h->g.PZ * h->g.PY * h->g.Hx;
-    if (cudaMalloc(&X.xbox, 4 * X.xbox_stride * sizeof(float)) != cudaSuccess) { h->err = "exchange: cudaMalloc column inbox"; return GB25_ERR_ALLOC; }
-    cudaMemset(X.xbox, 0, 4 * X.xbox_stride * sizeof(float));
+    if (cudaMalloc(&X.xbox, 4 * X.xbox_stride * sizeof(real)) != cudaSuccess) { h->err = "exchange: cudaMalloc column inbox"; return GB25_ERR_ALLOC; }
+    cudaMemset(X.xbox, 0, 4 * X.xbox_stride * sizeof(real));
   }
   return GB25_OK;
 }
@@ -347,7 +347,7 @@ extern "C" int gb25_exchange_export(gb25_handle* h, void* blob) {
   ExBlob b; memset(&b, 0, sizeof b);
   Exchange& X = h->ex;
   { const int rc = exchange_alloc_windows(h); if (rc != GB25_OK) return rc; }
-  float* tab[EX_NF];
+  real* tab[EX_NF];
   exchange_table(h, tab);
   for (int q = 0; q < EX_NF; q++) {
     cudaError_t e = cudaIpcGetMemHandle(&b.fld[q], tab[q]);
@@ -380,7 +380,7 @@ extern "C" int gb25_exchange_connect(gb25_handle* h, const void* blobs, int nran
   // map every distinct peer once
   std::vector<ExPeer> mapped(nranks);
   std::vector<char> have(nranks, 0);
-  float* mine[EX_NF];
+  real* mine[EX_NF];
   exchange_table(h, mine);
   for (int s = 0; s < EX_NSLOT; s++) {
     const int r = want[s];
@@ -396,7 +396,7 @@ extern "C" int gb25_exchange_connect(gb25_handle* h, const void* blobs, int nran
           void* ptr = nullptr;
           cudaError_t e = cudaIpcOpenMemHandle(&ptr, B[r].fld[q], cudaIpcMemLazyEnablePeerAccess);
           if (e != cudaSuccess) { h->err = std::string("gb25_exchange_connect: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); return GB25_ERR_COMM; }
-          X.opened.push_back(ptr); p.fld[q] = (float*)ptr;
+          X.opened.push_back(ptr); p.fld[q] = (real*)ptr;
         }
         void* ptr = nullptr;
         cudaError_t e = cudaIpcOpenMemHandle(&ptr, B[r].flags, cudaIpcMemLazyEnablePeerAccess);

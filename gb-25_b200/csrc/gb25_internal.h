@@ -10,7 +10,7 @@
 
 // flat = 1: a 2-D field riding in a batch of 3-D fields; zdone = 1: the z halos of the interior rows were already written
 // by the kernel that produced the field (corrector, tracer epilogue); zdone = 2: except the wall row Ny+1 of a Face-y field
-struct HaloSpec { float* a; int lx, ly, lz; float sign; int flat; int zdone; };
+struct HaloSpec { real* a; int lx, ly, lz; real sign; int flat; int zdone; };
 
 // ---- multi-GPU halo exchange over peer-mapped (CUDA IPC) memory, one process per GPU (gb25_exchange.cu)
 // exported allocations: both halves of the double-buffered 3-D state (all tiles flip in lockstep, so a tile's current
@@ -18,12 +18,12 @@ struct HaloSpec { float* a; int lx, ly, lz; float sign; int flat; int zdone; };
 // EX_XBOX: the column inbox (west / east strips arrive packed, see k_push_cols_packed)
 enum ExField { EX_U = 0, EX_V, EX_T, EX_S, EX_ETA, EX_BU, EX_BV, EX_GU, EX_GV, EX_U2, EX_V2, EX_T2, EX_S2, EX_XBOX, EX_NF };
 enum ExSlot { SLOT_W = 0, SLOT_E, SLOT_S, SLOT_N, SLOT_FOLD, SLOT_FOLD2, EX_NSLOT };
-struct ExPeer { float* fld[EX_NF]; int* flags; int rank; };
+struct ExPeer { real* fld[EX_NF]; int* flags; int rank; };
 struct Exchange {
   bool on = false;
   int nranks = 1, rank = 0;
   int* flags = nullptr;          // local inbox: EX_NSLOT sequence numbers written by the neighbours + 1 error word
-  float* xbox = nullptr;         // local column inbox: [seq parity][from west, from east][field slot][plane][row][Hx]
+  real* xbox = nullptr;         // local column inbox: [seq parity][from west, from east][field slot][plane][row][Hx]
   size_t xbox_stride = 0;        // floats per (parity, direction) box
   ExPeer to[EX_NSLOT];           // the tile lying in that direction (destination of my pushes); rank < 0: none
   int from_mask_y = 0, from_mask_x = 0, from_mask_fold = 0;   // slots I receive on in each phase
@@ -48,25 +48,25 @@ struct gb25_handle {
   int device = 0;
   std::vector<float> weights;
   std::vector<void*> allocs;
-  float* field_ptr[GB25_FIELD_COUNT];
+  real* field_ptr[GB25_FIELD_COUNT];
   // scratch 3-D arrays shared by the v2 kernels: vorticity (F,F,C), delta_x(Ax u) and delta_y(Ay v) at (C,C,C)
-  float *zeta = nullptr, *dxU = nullptr, *dyV = nullptr;
-  float *us2 = nullptr, *vs2 = nullptr;   // 2-D: column sums of the AB2-updated, masked velocities (fused path)
-  float *corr_u = nullptr, *corr_v = nullptr;   // 2-D: unmasked barotropic transports for the streamed corrector
-  float* carry[4] = {nullptr, nullptr, nullptr, nullptr};   // 2-D: vertical flux through the top face of the topmost generic cell (u, v, T, S)
+  real *zeta = nullptr, *dxU = nullptr, *dyV = nullptr;
+  real *us2 = nullptr, *vs2 = nullptr;   // 2-D: column sums of the AB2-updated, masked velocities (fused path)
+  real *corr_u = nullptr, *corr_v = nullptr;   // 2-D: unmasked barotropic transports for the streamed corrector
+  real* carry[4] = {nullptr, nullptr, nullptr, nullptr};   // 2-D: vertical flux through the top face of the topmost generic cell (u, v, T, S)
   // Double-buffered prognostic 3-D state.  The tendency kernels that end a step can apply the AB2 update of the NEXT step in
   // their epilogue (same dt, chi = cfg.chi): they read the state from state_buf[parity] and write the updated, masked state
   // into state_buf[1 - parity] (neighbouring tiles still read the old one), together with the column sums the barotropic
   // solve and the corrector need.  The next gb25_time_step with matching (dt, chi) then starts with a pointer swap instead of
   // the AB2 pass; anything else (another dt, an upload, an operator-level call) discards the speculation.
-  float* state_buf[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // [parity][u, v, T, S]
+  real* state_buf[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // [parity][u, v, T, S]
   int parity = 0;
-  float* spec2d[4] = {nullptr, nullptr, nullptr, nullptr};   // speculative GU, GV, sum dz u*, sum dz v* (committed by launch_commit_spec)
+  real* spec2d[4] = {nullptr, nullptr, nullptr, nullptr};   // speculative GU, GV, sum dz u*, sum dz v* (committed by launch_commit_spec)
   struct { bool valid = false; float dt = 0.f, chi = 0.f; bool zhalo = false; } spec;
   bool use_spec = true;
   bool use_zfold = true;               // corrector / tracer epilogue also write the z halos of the fields they produce
   // flux boundary conditions (row A7): 2-D device arrays [u, v, T, S][bottom, top], nullptr = no-flux
-  float* bflux[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  real* bflux[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   bool has_bflux = false;
   // clock (model.clock)
   double time = 0.0;
@@ -128,7 +128,7 @@ void exchange_baro_eta(Handle* h);
 void exchange_baro_uv(Handle* h);
 int exchange_check_timeout(Handle* h);
 void exchange_close(Handle* h);
-void exchange_table(Handle* h, float* tab[EX_NF]);   // the allocations behind ExField, in order
+void exchange_table(Handle* h, real* tab[EX_NF]);   // the allocations behind ExField, in order
 void launch_mask(Handle* h, bool uv_only);
 void launch_compute_w(Handle* h);
 void launch_compute_p(Handle* h);

@@ -7,58 +7,58 @@
 // =====================================================================================
 // Tracer tendencies (row A6): Gc = -div(U c), WENO5-Z upwind flux form, T and S together
 // =====================================================================================
-__device__ __forceinline__ void tracer_cell_generic(const DevGrid& g, const float* __restrict__ u, const float* __restrict__ v,
-                                                    const float* __restrict__ w, const float* __restrict__ T,
-                                                    const float* __restrict__ S, int i, int j, int k, float& outT, float& outS) {
+__device__ __forceinline__ void tracer_cell_generic(const DevGrid& g, const real* __restrict__ u, const real* __restrict__ v,
+                                                    const real* __restrict__ w, const real* __restrict__ T,
+                                                    const real* __restrict__ S, int i, int j, int k, real& outT, real& outS) {
   const int q2 = id2(g, i, j), PX = g.PX, n2 = g.n2;
   const size_t q3 = q2 + (size_t)n2 * (k + g.Hz - 1);
-  const float eps = g.eps;
+  const real eps = g.eps;
   const bool clear = (k - 1) > (int)g.knear[q2];
   const bool imm = g.immersed && !clear;
-  const float dz = g.dzc[k + g.Hz - 1];
-  const float* Tc = T + q3; const float* Sc = S + q3;
-  float dT = 0.f, dS = 0.f;
+  const real dz = g.dzc[k + g.Hz - 1];
+  const real* Tc = T + q3; const real* Sc = S + q3;
+  real dT = R(0.), dS = R(0.);
   // ---- x faces i (e=0) and i+1 (e=1)
-  float fT[2], fS[2];
+  real fT[2], fS[2];
 #pragma unroll
   for (int e = 0; e < 2; e++) {
-    const float vel = u[q3 + e];
-    const float area = g.dyfc[q2 + e] * dz;
+    const real vel = u[q3 + e];
+    const real area = g.dyfc[q2 + e] * dz;
     const int B = clear ? 3 : buf_from(g.fx3, g.fx2, q2 + e, k);
     const bool masked = imm && (k <= (int)g.kb[q2 + e] || k <= (int)g.kb[q2 + e - 1]);
-    const bool left = vel > 0.f;
-    fT[e] = masked ? 0.f : area * vel * recon_mem(Tc + e, 1, B, left, eps);
-    fS[e] = masked ? 0.f : area * vel * recon_mem(Sc + e, 1, B, left, eps);
+    const bool left = vel > R(0.);
+    fT[e] = masked ? R(0.) : area * vel * recon_mem(Tc + e, 1, B, left, eps);
+    fS[e] = masked ? R(0.) : area * vel * recon_mem(Sc + e, 1, B, left, eps);
   }
   dT = fT[1] - fT[0]; dS = fS[1] - fS[0];
   // ---- y faces j and j+1
 #pragma unroll
   for (int e = 0; e < 2; e++) {
-    const float vel = v[q3 + e * PX];
-    const float area = g.dxcf[q2 + e * PX] * dz;
+    const real vel = v[q3 + e * PX];
+    const real area = g.dxcf[q2 + e * PX] * dz;
     const int B = clear ? 3 : buf_from(g.fy3, g.fy2, q2 + e * PX, k);
     const bool wall = y_outside(g, j + e) || y_outside(g, j + e - 1);
     const bool masked = imm && !wall && (k <= (int)g.kb[q2 + e * PX] || k <= (int)g.kb[q2 + (e - 1) * PX]);
-    const bool left = vel > 0.f;
-    fT[e] = masked ? 0.f : area * vel * recon_mem(Tc + e * PX, PX, B, left, eps);
-    fS[e] = masked ? 0.f : area * vel * recon_mem(Sc + e * PX, PX, B, left, eps);
+    const bool left = vel > R(0.);
+    fT[e] = masked ? R(0.) : area * vel * recon_mem(Tc + e * PX, PX, B, left, eps);
+    fS[e] = masked ? R(0.) : area * vel * recon_mem(Sc + e * PX, PX, B, left, eps);
   }
   dT += fT[1] - fT[0]; dS += fS[1] - fS[0];
   // ---- z faces k and k+1
   const int kbc = g.kb[q2];
-  const float az = g.azcc[q2];
+  const real az = g.azcc[q2];
 #pragma unroll
   for (int e = 0; e < 2; e++) {
     const int kk = k + e;
-    const float vel = w[q3 + (size_t)e * n2];
+    const real vel = w[q3 + (size_t)e * n2];
     const int B = zbuf(g, kbc, kk, 3);
     const bool masked = g.immersed && kk != 1 && kk != g.Nz + 1 && (kk - 1 <= kbc);
-    const bool left = vel > 0.f;
-    fT[e] = masked ? 0.f : az * vel * recon_mem(Tc + e * n2, n2, B, left, eps);
-    fS[e] = masked ? 0.f : az * vel * recon_mem(Sc + e * n2, n2, B, left, eps);
+    const bool left = vel > R(0.);
+    fT[e] = masked ? R(0.) : az * vel * recon_mem(Tc + e * n2, n2, B, left, eps);
+    fS[e] = masked ? R(0.) : az * vel * recon_mem(Sc + e * n2, n2, B, left, eps);
   }
   dT += fT[1] - fT[0]; dS += fS[1] - fS[0];
-  const float rV = 1.f / (az * dz);
+  const real rV = R(1.) / (az * dz);
   outT = -(rV * dT);
   outS = -(rV * dS);
 }
@@ -67,48 +67,48 @@ __device__ __forceinline__ void tracer_cell_generic(const DevGrid& g, const floa
 // Returns G; *ftop receives the (masked) flux through the top face so that a k-marching caller can carry it.
 // (takes the grid descriptor through a global-memory pointer: a by-reference kernel parameter would be
 // copied to the local stack at every call of a non-inlined function)
-static __device__ __noinline__ float tracer_cell_generic1(const DevGrid* __restrict__ gp, const float* __restrict__ u,
-                                                          const float* __restrict__ v, const float* __restrict__ w,
-                                                          const float* __restrict__ T, int i, int j, int k, float* ftop) {
+static __device__ __noinline__ real tracer_cell_generic1(const DevGrid* __restrict__ gp, const real* __restrict__ u,
+                                                          const real* __restrict__ v, const real* __restrict__ w,
+                                                          const real* __restrict__ T, int i, int j, int k, real* ftop) {
   const DevGrid& g = *gp;
   const int q2 = id2(g, i, j), PX = g.PX, n2 = g.n2;
   const size_t q3 = q2 + (size_t)n2 * (k + g.Hz - 1);
-  const float eps = g.eps;
+  const real eps = g.eps;
   const bool clear = (k - 1) > (int)g.knear[q2];
   const bool imm = g.immersed && !clear;
-  const float dz = g.dzc[k + g.Hz - 1];
-  const float* Tc = T + q3;
-  float fT[2];
+  const real dz = g.dzc[k + g.Hz - 1];
+  const real* Tc = T + q3;
+  real fT[2];
 #pragma unroll
   for (int e = 0; e < 2; e++) {
-    const float vel = u[q3 + e];
+    const real vel = u[q3 + e];
     const int B = clear ? 3 : buf_from(g.fx3, g.fx2, q2 + e, k);
     const bool masked = imm && (k <= (int)g.kb[q2 + e] || k <= (int)g.kb[q2 + e - 1]);
-    fT[e] = masked ? 0.f : g.dyfc[q2 + e] * dz * vel * recon_mem(Tc + e, 1, B, vel > 0.f, eps);
+    fT[e] = masked ? R(0.) : g.dyfc[q2 + e] * dz * vel * recon_mem(Tc + e, 1, B, vel > R(0.), eps);
   }
-  float dT = fT[1] - fT[0];
+  real dT = fT[1] - fT[0];
 #pragma unroll
   for (int e = 0; e < 2; e++) {
-    const float vel = v[q3 + e * PX];
+    const real vel = v[q3 + e * PX];
     const int B = clear ? 3 : buf_from(g.fy3, g.fy2, q2 + e * PX, k);
     const bool wall = y_outside(g, j + e) || y_outside(g, j + e - 1);
     const bool masked = imm && !wall && (k <= (int)g.kb[q2 + e * PX] || k <= (int)g.kb[q2 + (e - 1) * PX]);
-    fT[e] = masked ? 0.f : g.dxcf[q2 + e * PX] * dz * vel * recon_mem(Tc + e * PX, PX, B, vel > 0.f, eps);
+    fT[e] = masked ? R(0.) : g.dxcf[q2 + e * PX] * dz * vel * recon_mem(Tc + e * PX, PX, B, vel > R(0.), eps);
   }
   dT += fT[1] - fT[0];
   const int kbc = g.kb[q2];
-  const float az = g.azcc[q2];
+  const real az = g.azcc[q2];
 #pragma unroll
   for (int e = 0; e < 2; e++) {
     const int kk = k + e;
-    const float vel = w[q3 + (size_t)e * n2];
+    const real vel = w[q3 + (size_t)e * n2];
     const int B = zbuf(g, kbc, kk, 3);
     const bool masked = g.immersed && kk != 1 && kk != g.Nz + 1 && (kk - 1 <= kbc);
-    fT[e] = masked ? 0.f : az * vel * recon_mem(Tc + e * n2, n2, B, vel > 0.f, eps);
+    fT[e] = masked ? R(0.) : az * vel * recon_mem(Tc + e * n2, n2, B, vel > R(0.), eps);
   }
   dT += fT[1] - fT[0];
   *ftop = fT[1];
-  return -((1.f / (az * dz)) * dT);
+  return -((R(1.) / (az * dz)) * dT);
 }
 
 // =====================================================================================
@@ -119,23 +119,23 @@ static __device__ __noinline__ float tracer_cell_generic1(const DevGrid* __restr
 // (a, b) below are offsets along the component's own / cross horizontal direction.
 // =====================================================================================
 template <int DIR>
-__device__ __forceinline__ float momentum_G(const DevGrid& g, const float* __restrict__ own, const float* __restrict__ oth,
-                                            const float* __restrict__ w, const float* __restrict__ p, int i, int j, int k,
-                                            float* wtop = nullptr) {
+__device__ __forceinline__ real momentum_G(const DevGrid& g, const real* __restrict__ own, const real* __restrict__ oth,
+                                            const real* __restrict__ w, const real* __restrict__ p, int i, int j, int k,
+                                            real* wtop = nullptr) {
   const int PX = g.PX, n2 = g.n2;
   const int sO = DIR == 0 ? 1 : PX, sC = DIR == 0 ? PX : 1;
-  const float* __restrict__ M1 = DIR == 0 ? g.dxfc : g.dycf;  // own-direction spacing at the own-velocity point
-  const float* __restrict__ M2 = DIR == 0 ? g.dxcf : g.dyfc;  // own-direction spacing at the other-velocity point
-  const float* __restrict__ M3 = DIR == 0 ? g.dyfc : g.dxcf;  // cross spacing at the own-velocity point
-  const float* __restrict__ M4 = DIR == 0 ? g.dycf : g.dxfc;  // cross spacing at the other-velocity point
-  const float* __restrict__ AZo = DIR == 0 ? g.azfc : g.azcf;
+  const real* __restrict__ M1 = DIR == 0 ? g.dxfc : g.dycf;  // own-direction spacing at the own-velocity point
+  const real* __restrict__ M2 = DIR == 0 ? g.dxcf : g.dyfc;  // own-direction spacing at the other-velocity point
+  const real* __restrict__ M3 = DIR == 0 ? g.dyfc : g.dxcf;  // cross spacing at the own-velocity point
+  const real* __restrict__ M4 = DIR == 0 ? g.dycf : g.dxfc;  // cross spacing at the other-velocity point
+  const real* __restrict__ AZo = DIR == 0 ? g.azfc : g.azcf;
   const short* fO3 = DIR == 0 ? g.fx3 : g.fy3; const short* fO2 = DIR == 0 ? g.fx2 : g.fy2;
   const short* cC3 = DIR == 0 ? g.cy3 : g.cx3; const short* cC2 = DIR == 0 ? g.cy2 : g.cx2;
   const int q2 = id2(g, i, j);
   const size_t q3 = q2 + (size_t)n2 * (k + g.Hz - 1);
-  const float* O = own + q3; const float* X = oth + q3;
-  const float eps = g.eps;
-  const float dz = g.dzc[k + g.Hz - 1];
+  const real* O = own + q3; const real* X = oth + q3;
+  const real eps = g.eps;
+  const real dz = g.dzc[k + g.Hz - 1];
   const bool clear = (k - 1) > (int)g.knear[q2];
   const bool imm = g.immersed && !clear;
 #define OF(a, b) ((a) * sO + (b) * sC)
@@ -144,67 +144,67 @@ __device__ __forceinline__ float momentum_G(const DevGrid& g, const float* __res
     const int jj = DIR == 0 ? j + b : j + a;
     return kk < 1 || kk > g.Nz || y_outside(g, jj) || kk <= (int)g.kb[q2 + OF(a, b)];
   };
-  const float own0 = O[0];
-  const float m1 = M1[q2];
+  const real own0 = O[0];
+  const real m1 = M1[q2];
 
   // ---------------- horizontal: -(other-hat) * zeta^R  (vorticity flux)
-  const float x00 = M2[q2 + OF(0, 0)] * X[OF(0, 0)], x01 = M2[q2 + OF(0, 1)] * X[OF(0, 1)];
-  const float xm0 = M2[q2 + OF(-1, 0)] * X[OF(-1, 0)], xm1 = M2[q2 + OF(-1, 1)] * X[OF(-1, 1)];
-  const float oavg = ((xm0 + xm1) * 0.5f + (x00 + x01) * 0.5f) * 0.5f;
-  const float ohat = oavg / m1;
-  float zq[6], zs[6], zr[6];
+  const real x00 = M2[q2 + OF(0, 0)] * X[OF(0, 0)], x01 = M2[q2 + OF(0, 1)] * X[OF(0, 1)];
+  const real xm0 = M2[q2 + OF(-1, 0)] * X[OF(-1, 0)], xm1 = M2[q2 + OF(-1, 1)] * X[OF(-1, 1)];
+  const real oavg = ((xm0 + xm1) * R(0.5) + (x00 + x01) * R(0.5)) * R(0.5);
+  const real ohat = oavg / m1;
+  real zq[6], zs[6], zr[6];
 #pragma unroll
   for (int m = 0; m < 6; m++) {
     const int b = m - 2;
-    float d1 = M4[q2 + OF(0, b)] * X[OF(0, b)] - M4[q2 + OF(-1, b)] * X[OF(-1, b)];
-    float d2 = M1[q2 + OF(0, b)] * O[OF(0, b)] - M1[q2 + OF(0, b - 1)] * O[OF(0, b - 1)];
+    real d1 = M4[q2 + OF(0, b)] * X[OF(0, b)] - M4[q2 + OF(-1, b)] * X[OF(-1, b)];
+    real d2 = M1[q2 + OF(0, b)] * O[OF(0, b)] - M1[q2 + OF(0, b - 1)] * O[OF(0, b - 1)];
     if (imm && g.cond_diff) {
       const bool c00 = inact(0, b, k), c0m = inact(0, b - 1, k), cm0 = inact(-1, b, k), cmm = inact(-1, b - 1, k);
-      if ((c00 && c0m) || (cm0 && cmm)) d1 = 0.f;   // inactive other-velocity nodes
-      if ((c00 && cm0) || (c0m && cmm)) d2 = 0.f;   // inactive own-velocity nodes
+      if ((c00 && c0m) || (cm0 && cmm)) d1 = R(0.);   // inactive other-velocity nodes
+      if ((c00 && cm0) || (c0m && cmm)) d2 = R(0.);   // inactive own-velocity nodes
     }
     zq[m] = (d1 - d2) / g.azff[q2 + OF(0, b)];
-    zs[m] = (O[OF(0, b - 1)] + O[OF(0, b)]) * 0.5f;
-    zr[m] = (X[OF(-1, b)] + X[OF(0, b)]) * 0.5f;
+    zs[m] = (O[OF(0, b - 1)] + O[OF(0, b)]) * R(0.5);
+    zr[m] = (X[OF(-1, b)] + X[OF(0, b)]) * R(0.5);
   }
   const int Bc = clear ? 3 : buf_from(cC3, cC2, q2, k);
-  const float zR = recon_w_vs(zq, zs, zr, Bc, ohat > 0.f, eps);
-  const float Hterm = -ohat * zR;
+  const real zR = recon_w_vs(zq, zs, zr, Bc, ohat > R(0.), eps);
+  const real Hterm = -ohat * zR;
 
   // ---------------- divergence flux (self-upwinding) and kinetic-energy gradient along the own direction
-  float dOw[6], dv[6], dK[6], sK[6], dOt[6];
+  real dOw[6], dv[6], dK[6], sK[6], dOt[6];
 #pragma unroll
   for (int m = 0; m < 6; m++) {
     const int a = m - 3;
-    const float o0 = O[OF(a, 0)], o1 = O[OF(a + 1, 0)];
+    const real o0 = O[OF(a, 0)], o1 = O[OF(a + 1, 0)];
     dOw[m] = M3[q2 + OF(a + 1, 0)] * dz * o1 - M3[q2 + OF(a, 0)] * dz * o0;
     dOt[m] = M2[q2 + OF(a, 1)] * dz * X[OF(a, 1)] - M2[q2 + OF(a, 0)] * dz * X[OF(a, 0)];
     dv[m] = DIR == 0 ? dOw[m] + dOt[m] : dOt[m] + dOw[m];
-    dK[m] = o1 * o1 * 0.5f - o0 * o0 * 0.5f;
-    sK[m] = (o0 + o1) * 0.5f;
+    dK[m] = o1 * o1 * R(0.5) - o0 * o0 * R(0.5);
+    sK[m] = (o0 + o1) * R(0.5);
   }
   const int Bf = clear ? 3 : buf_from(fO3, fO2, q2, k);
   const int Bs = clear ? 2 : (k > (int)fO2[q2] ? 2 : 1);
-  const bool lown = own0 > 0.f;
-  const float dvs = sym4(dOt[1], dOt[2], dOt[3], dOt[4], Bs);
-  const float duR = recon_w_fs(dOw, dv, Bf, lown, eps);
-  const float Phi = own0 * (dvs + duR);
-  const float dKo = recon_w_fs(dK, sK, Bf, lown, eps);
+  const bool lown = own0 > R(0.);
+  const real dvs = sym4(dOt[1], dOt[2], dOt[3], dOt[4], Bs);
+  const real duR = recon_w_fs(dOw, dv, Bf, lown, eps);
+  const real Phi = own0 * (dvs + duR);
+  const real dKo = recon_w_fs(dK, sK, Bf, lown, eps);
   // cross kinetic-energy gradient, centred along the cross direction
   const int Bsc = clear ? 2 : (k > (int)cC2[q2] ? 2 : 1);
-  float kc[4];
+  real kc[4];
 #pragma unroll
   for (int m = 0; m < 4; m++) {
     const int b = m - 1;
-    const float t0 = X[OF(0, b)], t1 = X[OF(-1, b)];
-    kc[m] = t0 * t0 * 0.5f - t1 * t1 * 0.5f;
+    const real t0 = X[OF(0, b)], t1 = X[OF(-1, b)];
+    kc[m] = t0 * t0 * R(0.5) - t1 * t1 * R(0.5);
   }
-  const float dKc = sym4(kc[0], kc[1], kc[2], kc[3], Bsc);
-  const float Bterm = (dKo + dKc) / m1;
+  const real dKc = sym4(kc[0], kc[1], kc[2], kc[3], Bsc);
+  const real Bterm = (dKo + dKc) / m1;
 
   // ---------------- vertical advection: delta_z ( w~ * own^R )
   const int kb0 = g.kb[q2], kbm = g.kb[q2 + OF(-1, 0)];
-  float Wf[2];
+  real Wf[2];
 #pragma unroll
   for (int e = 0; e < 2; e++) {
     const int kk = k + e;
@@ -214,20 +214,20 @@ __device__ __forceinline__ float momentum_G(const DevGrid& g, const float* __res
       if (DIR == 1) wall = y_outside(g, j) || y_outside(g, j - 1);
       masked = !wall && (kk - 1 <= kb0 || kk - 1 <= kbm);
     }
-    const float* wl = w + q3 + (size_t)e * n2;
+    const real* wl = w + q3 + (size_t)e * n2;
     const int Bw = (g.immersed && kk > g.Nz) ? 1 : (kk > (int)fO2[q2] ? 2 : 1);
-    const float wt = sym4(g.azcc[q2 + OF(-2, 0)] * wl[OF(-2, 0)], g.azcc[q2 + OF(-1, 0)] * wl[OF(-1, 0)],
+    const real wt = sym4(g.azcc[q2 + OF(-2, 0)] * wl[OF(-2, 0)], g.azcc[q2 + OF(-1, 0)] * wl[OF(-1, 0)],
                           g.azcc[q2 + OF(0, 0)] * wl[OF(0, 0)], g.azcc[q2 + OF(1, 0)] * wl[OF(1, 0)], Bw);
     const int Bz = zbuf(g, kb0, kk, 3);
-    const float oR = recon_mem(O + (size_t)e * n2, n2, Bz, wt > 0.f, eps);
-    Wf[e] = masked ? 0.f : wt * oR;
+    const real oR = recon_mem(O + (size_t)e * n2, n2, Bz, wt > R(0.), eps);
+    Wf[e] = masked ? R(0.) : wt * oR;
   }
   if (wtop) *wtop = Wf[1];   // (masked) vertical momentum flux through the top face, for k-marching callers
-  const float Vterm = (1.f / (AZo[q2] * dz)) * (Phi + (Wf[1] - Wf[0]));
+  const real Vterm = (R(1.) / (AZo[q2] * dz)) * (Phi + (Wf[1] - Wf[0]));
 
   // ---------------- Coriolis (enstrophy conserving, optionally active-cell weighted)
-  const float fbar = (g.fff[q2] + g.fff[q2 + OF(0, 1)]) * 0.5f;
-  float avg = oavg;
+  const real fbar = (g.fff[q2] + g.fff[q2 + OF(0, 1)]) * R(0.5);
+  real avg = oavg;
   if (g.coriolis_scheme == 1 && !clear) {
     // other-velocity nodes are Faces along the cross direction: peripheral = cell (a,b) or (a,b-1) inactive
     int nact = 0;
@@ -235,14 +235,14 @@ __device__ __forceinline__ float momentum_G(const DevGrid& g, const float* __res
     for (int a = -1; a <= 0; a++)
 #pragma unroll
       for (int b = 0; b <= 1; b++) nact += !(inact(a, b, k) || inact(a, b - 1, k));
-    avg = nact == 0 ? 0.f : oavg / ((float)nact * 0.25f);
+    avg = nact == 0 ? R(0.) : oavg / ((real)nact * R(0.25));
   }
-  const float ct = fbar * avg / m1;
-  const float cor = DIR == 0 ? -ct : ct;
+  const real ct = fbar * avg / m1;
+  const real cor = DIR == 0 ? -ct : ct;
   // ---------------- hydrostatic pressure gradient
-  const float* pc = p + q3;
-  float dp = (pc[0] - pc[OF(-1, 0)]) / m1;
-  if (imm && g.cond_diff && (inact(0, 0, k) || inact(-1, 0, k))) dp = 0.f;
+  const real* pc = p + q3;
+  real dp = (pc[0] - pc[OF(-1, 0)]) / m1;
+  if (imm && g.cond_diff && (inact(0, 0, k) || inact(-1, 0, k))) dp = R(0.);
 #undef OF
   return -(Hterm + Vterm + Bterm) - cor - dp;
 }

@@ -784,7 +784,10 @@ k_tracer_tma(DevGrid g, const __grid_constant__ TmaMaps5 tm, const __grid_consta
   const float* __restrict__ carry = tr == 0 ? carry0 : carry1;
   float* __restrict__ Tn = tr == 0 ? ab.next[0] : ab.next[1];
   const int lx = 2 * tx, ly = 2 * ty;                       // tile-local column / row of the patch
-  const int ic = min(i0 + lx, g.Nx - 1), jc = min(j0 + ly, g.Ny - 1);   // clamped patch origin (for the hoisted loads)
+  // clamped patch origin (for the hoisted loads).  A patch may start on the last row when Ny is odd: its second row is then
+  // the halo row Ny + 1, which exists in memory and is never stored (vrow); clamping the origin to Ny - 1 instead would make
+  // the patch read rows (Ny, Ny + 1) from shared memory but address rows (Ny - 1, Ny) in global memory.
+  const int ic = min(i0 + lx, g.Nx - 1), jc = min(j0 + ly, g.Ny);
   const bool vx = (i0 + lx + 1) <= g.Nx;
   bool vrow[2] = {vx && (j0 + ly) <= g.Ny, vx && (j0 + ly + 1) <= g.Ny};
   const int q2 = id2(g, ic, jc);

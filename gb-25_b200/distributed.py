@@ -54,7 +54,8 @@ def connect(model, dist):
 
 
 def sharded_baroclinic_instability_model(arch, Nx, Ny, Nz, *, Δt, grid_type="simple_lat_lon", Rx=None, Ry=None,
-                                         rank=None, dist=None, halo=(8, 8, 8), physics=None, global_size=False):
+                                         rank=None, dist=None, halo=(8, 8, 8), physics=None, global_size=False,
+                                         float_type=np.float32):
     """The model of ``baroclinic_instability_model`` on tile ``rank`` of an (Rx, Ry) partition.  ``Nx, Ny`` are the
     PER-TILE interior sizes (the reference's scaling scripts also fix the tile, e.g. sharding/alps_scaling_test.jl:34)
     unless ``global_size`` is set."""
@@ -68,7 +69,7 @@ def sharded_baroclinic_instability_model(arch, Nx, Ny, Nz, *, Δt, grid_type="si
     gNx, gNy = (Nx, Ny) if global_size else (Nx * Rx, Ny * Ry)
     gg = M.make_grid(gNx, gNy, Nz, halo, grid_type)
     tile = tile_grid(gg, Rx, Ry, rx, ry)
-    model = M.HydrostaticFreeSurfaceModel(arch, tile, physics, partition=(Rx, Ry, rx, ry))
+    model = M.HydrostaticFreeSurfaceModel(arch, tile, physics, partition=(Rx, Ry, rx, ry), float_type=float_type)
     model.partition = (Rx, Ry, rx, ry)
     model.global_grid = gg
     model.dist = dist

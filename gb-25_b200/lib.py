@@ -16,6 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # GB25_LIB selects another in-tree build of the same library (kernel experiments: gb25_b200.build --suffix); it is never
 # a different implementation, and a missing file still fails loudly.
 LIB_PATH = os.environ.get("GB25_LIB") or os.path.join(_HERE, "csrc", "libgb25cuda.so")
+# the Float64 build of the same sources (include/gb25cuda.h: gb25_real = double); `--float-type Float64` of the reference CLI
+LIB_PATH_F64 = os.environ.get("GB25_LIB_F64") or os.path.join(_HERE, "csrc", "libgb25cuda_f64.so")
 
 GB25_OK, GB25_ERR_INVALID, GB25_ERR_NO_DEVICE, GB25_ERR_CUDA, GB25_ERR_ALLOC, GB25_ERR_COMM = 0, -1, -2, -3, -4, -5
 
@@ -36,7 +38,7 @@ FIELD_LOC = {
 }
 
 EXPORTED_SYMBOLS = (
-    "gb25_abi_version", "gb25_create", "gb25_destroy", "gb25_last_error", "gb25_clear_error",
+    "gb25_abi_version", "gb25_real_bytes", "gb25_create", "gb25_destroy", "gb25_last_error", "gb25_clear_error",
     "gb25_field_shape", "gb25_set_field", "gb25_get_field", "gb25_set_clock", "gb25_get_clock",
     "gb25_interior_shape", "gb25_set_interior", "gb25_get_interior", "gb25_set_fields", "gb25_get_fields",
     "gb25_initialize", "gb25_update_state", "gb25_first_time_step", "gb25_time_step", "gb25_loop",
@@ -70,21 +72,28 @@ _GRID_PTRS = ("dx_cc", "dx_fc", "dx_cf", "dx_ff", "dy_cc", "dy_fc", "dy_cf", "dy
 
 
 class gb25_grid(C.Structure):
-    _fields_ = [(n, C.POINTER(C.c_float)) for n in _GRID_PTRS]
+    _fields_ = [(n, C.c_void_p) for n in _GRID_PTRS]      # const gb25_real* (const float* for avg_weights)
 
 
-_lib = None
+_libs = {}
 
 
-def load():
-    """Load libgb25cuda.so (in-tree).  Raises if it has not been built: there is no fallback."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def load(float_type=np.float32):
+    """Load libgb25cuda.so (Float32) or libgb25cuda_f64.so (Float64), both in-tree.  Raises if the library has not been
+    built: there is no fallback."""
+    ft = np.dtype(float_type)
+    if ft in _libs:
+        return _libs[ft]
+    path = LIB_PATH if ft == np.float32 else LIB_PATH_F64
+    if ft not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise ValueError("float_type must be Float32 or Float64")
+    if not os.path.exists(path):
         raise Gb25Error(GB25_ERR_NO_DEVICE,
-                        f"{LIB_PATH} not found — build it with __graft_entry__.build(); there is no CPU fallback")
-    lib = C.CDLL(LIB_PATH)
+                        f"{path} not found — build it with __graft_entry__.build(); there is no CPU fallback")
+    lib = C.CDLL(path)
+    lib.gb25_real_bytes.restype = C.c_int
+    if lib.gb25_real_bytes() != ft.itemsize:
+        raise Gb25Error(GB25_ERR_INVALID, f"{path} is not the {ft} build")
     H = C.c_void_p
     lib.gb25_abi_version.restype = C.c_int
     lib.gb25_create.argtypes = [C.POINTER(gb25_config), C.POINTER(gb25_grid), C.POINTER(H)]
@@ -119,7 +128,7 @@ def load():
     lib.gb25_exchange_connect.argtypes = [H, C.c_void_p, C.c_int]
     lib.gb25_exchange_connect_local.argtypes = [C.POINTER(H), C.c_int]
     lib.gb25_loop_all.argtypes = [C.POINTER(H), C.c_int, C.c_float, C.c_int]
-    _lib = lib
+    _libs[ft] = lib
     return lib
 
 
@@ -130,8 +139,9 @@ def _f32(a):
 class Handle:
     """Owns one gb25_handle (one tile on one GPU)."""
 
-    def __init__(self, grid, physics, dtau_frac, weights, device=-1, partition=(1, 1, 0, 0)):
-        self.lib = load()
+    def __init__(self, grid, physics, dtau_frac, weights, device=-1, partition=(1, 1, 0, 0), float_type=np.float32):
+        self.dtype = np.dtype(float_type)
+        self.lib = load(self.dtype)
         self._keep = {}
         cfg = gb25_config()
         cfg.Nx, cfg.Ny, cfg.Nz, cfg.Hx, cfg.Hy, cfg.Hz = grid.Nx, grid.Ny, grid.Nz, grid.Hx, grid.Hy, grid.Hz
@@ -154,9 +164,11 @@ class Handle:
             if a is None:
                 setattr(g, name, None)
                 continue
-            a = _f32(a)
+            # grid products are Float32 values on the host (the reference model's grid type); the Float64 build receives
+            # them promoted, exactly as the Float64 oracle does
+            a = _f32(a) if name == "avg_weights" else np.ascontiguousarray(_f32(a).astype(self.dtype))
             self._keep[name] = a
-            setattr(g, name, a.ctypes.data_as(C.POINTER(C.c_float)))
+            setattr(g, name, a.ctypes.data)
         h = C.c_void_p()
         rc = self.lib.gb25_create(C.byref(cfg), C.byref(g), C.byref(h))
         if rc != GB25_OK:
@@ -188,15 +200,18 @@ class Handle:
         self.check(self.lib.gb25_field_shape(self.h, FIELD_ID[name], s))
         return (s[2], s[1], s[0])          # NumPy (z, y, x) view of the Julia (x, y, z) parent
 
+    def _arr(self, a):
+        return np.ascontiguousarray(a, dtype=self.dtype)
+
     def set_field(self, name, parent):
-        a = _f32(parent)
+        a = self._arr(parent)
         if a.shape != self.field_shape(name):
             raise ValueError(f"{name}: parent shape {a.shape} != {self.field_shape(name)}")
         self.check(self.lib.gb25_set_field(self.h, FIELD_ID[name], a.ctypes.data))
 
     def get_field(self, name, out=None):
         if out is None:
-            out = np.empty(self.field_shape(name), dtype=np.float32)
+            out = np.empty(self.field_shape(name), dtype=self.dtype)
         self.check(self.lib.gb25_get_field(self.h, FIELD_ID[name], out.ctypes.data))
         return out
 
@@ -208,12 +223,12 @@ class Handle:
     def set_interior(self, name, values):
         """set!(model, name=values): interior-shaped upload, halos untouched."""
         shp = self.interior_shape(name)
-        a = _f32(np.broadcast_to(np.asarray(values, dtype=np.float32), shp))
+        a = self._arr(np.broadcast_to(np.asarray(values, dtype=self.dtype), shp))
         self.check(self.lib.gb25_set_interior(self.h, FIELD_ID[name], a.ctypes.data))
 
     def get_interior(self, name, out=None):
         if out is None:
-            out = np.empty(self.interior_shape(name), dtype=np.float32)
+            out = np.empty(self.interior_shape(name), dtype=self.dtype)
         self.check(self.lib.gb25_get_interior(self.h, FIELD_ID[name], out.ctypes.data))
         return out
 
@@ -223,8 +238,8 @@ class Handle:
         ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
         for x, a in zip(names, arrays):
             want = self.interior_shape(x) if interior else self.field_shape(x)
-            if a.shape != want or a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
-                raise ValueError(f"{x}: need a C-contiguous float32 array of shape {want}")
+            if a.shape != want or a.dtype != self.dtype or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"{x}: need a C-contiguous {self.dtype} array of shape {want}")
         self.check(fn(self.h, n, ids, ptrs, 1 if interior else 0))
 
     def set_fields(self, names, arrays, interior=False):
@@ -242,7 +257,7 @@ class Handle:
             return
         two_d = {"u": "U", "v": "V", "T": "eta", "S": "eta"}[name]
         shp = self.field_shape(two_d)[1:]
-        a = _f32(values)
+        a = self._arr(values)
         if a.shape != shp:
             raise ValueError(f"flux of {name}: need a 2-D parent of shape {shp}, got {a.shape}")
         self.check(self.lib.gb25_set_flux_boundary_condition(self.h, FIELD_ID[name], sd, a.ctypes.data))

@@ -85,14 +85,16 @@ class HydrostaticFreeSurfaceModel(ModelBase):
     """Device-resident model: the analogue of ``HydrostaticFreeSurfaceModel(; grid, free_surface, …)``
     (/root/reference/src/baroclinic_instability_model.jl:67-70) on the ``B200`` architecture."""
 
-    def __init__(self, arch, grid, physics=None, partition=(1, 1, 0, 0)):
+    def __init__(self, arch, grid, physics=None, partition=(1, 1, 0, 0), float_type=np.float32):
         if not isinstance(arch, B200):
             raise TypeError("arch must be B200(); libgb25cuda has no CPU architecture")
         self.arch = arch
         self.grid = grid
+        self.dtype = np.dtype(float_type)       # eltype(grid): Float32 (BASELINE) or Float64 (the reference CLI's default)
         self.physics = physics or PhysicsConfig()
         self.dtau_frac, self.weights = averaging_weights(self.physics.substeps)
-        self.handle = Handle(grid, self.physics, self.dtau_frac, self.weights, device=arch.device, partition=partition)
+        self.handle = Handle(grid, self.physics, self.dtau_frac, self.weights, device=arch.device, partition=partition,
+                             float_type=self.dtype)
         self.clock = Clock()
 
     # --- state access
@@ -309,7 +311,7 @@ def sync_states(m1, m2):
     for name in m1.field_names:
         p2 = m2.parent(name)
         s1 = m1.parent(name).shape
-        m1.set_parent(name, p2[:s1[0], :s1[1], :s1[2]].astype(np.float32))
+        m1.set_parent(name, p2[:s1[0], :s1[1], :s1[2]].astype(getattr(m1, "dtype", np.float32)))
 
 
 ALL_FIELD_NAMES = FIELD_NAMES

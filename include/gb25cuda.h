@@ -24,6 +24,19 @@ extern "C" {
 
 #define GB25_ABI_VERSION 1
 
+/* Scalar type of every field and grid array that crosses the boundary.  libgb25cuda.so is the Float32 build (BASELINE:
+ * Float32 cell-steps/s); libgb25cuda_f64.so is the same source compiled with -DGB25_F64 for `--float-type Float64`
+ * (/root/reference/src/arg_parsing.jl:28-31, the reference CLI's default): it runs the operator-per-kernel generation of the
+ * kernels in double precision; the TMA / packed-FP32x2 / persistent kernels exist in Float32 only.  gb25_real_bytes() tells
+ * the two apart at run time.  Model parameters (g, rho0, chi, dt, ...) stay `float` in both: the host model holds them in
+ * Float32 when it was built with a Float32 grid, and a Float64 host passes values that are exact in Float32 or accepts the
+ * rounding (the parity tests round them first). */
+#ifdef GB25_F64
+typedef double gb25_real;
+#else
+typedef float gb25_real;
+#endif
+
 typedef struct gb25_handle gb25_handle;
 
 typedef enum {
@@ -75,14 +88,14 @@ typedef struct {
  * Replaces what the kernels read from `grid` (grid.Δxᶠᶜᵃ, grid.Azᶜᶜᵃ, grid.z.cᵃᵃᶠ, …,
  * ibg.immersed_boundary.bottom_height) — built on the host by src/model_utils.jl:56-65,134-146. */
 typedef struct {
-  const float *dx_cc, *dx_fc, *dx_cf, *dx_ff;
-  const float *dy_cc, *dy_fc, *dy_cf, *dy_ff;
-  const float *az_cc, *az_fc, *az_cf, *az_ff;
-  const float *f_ff;            /* 2 Ω sin φ at (Face,Face): HydrostaticSphericalCoriolis           */
-  const float *z_f, *z_c;       /* face / centre heights                                            */
-  const float *dz_c, *dz_f;     /* Δz at centres (zf[k+1]-zf[k]) and at faces (zc[k]-zc[k-1])       */
-  const float *bottom_height;   /* GridFittedBottom height at (C,C), or NULL when not immersed       */
-  const float *avg_weights;     /* nsubsteps split-explicit averaging weights                        */
+  const gb25_real *dx_cc, *dx_fc, *dx_cf, *dx_ff;
+  const gb25_real *dy_cc, *dy_fc, *dy_cf, *dy_ff;
+  const gb25_real *az_cc, *az_fc, *az_cf, *az_ff;
+  const gb25_real *f_ff;            /* 2 Ω sin φ at (Face,Face): HydrostaticSphericalCoriolis           */
+  const gb25_real *z_f, *z_c;       /* face / centre heights                                            */
+  const gb25_real *dz_c, *dz_f;     /* Δz at centres (zf[k+1]-zf[k]) and at faces (zc[k]-zc[k-1])       */
+  const gb25_real *bottom_height;   /* GridFittedBottom height at (C,C), or NULL when not immersed       */
+  const float *avg_weights;         /* nsubsteps split-explicit averaging weights (always Float32)       */
 } gb25_grid;
 
 /* Field identifiers for gb25_set_field / gb25_get_field / gb25_field_shape.
@@ -99,6 +112,7 @@ typedef enum {
 } gb25_field;
 
 int gb25_abi_version(void);
+int gb25_real_bytes(void);                            /* 4: libgb25cuda.so, 8: libgb25cuda_f64.so */
 
 /* Construction / destruction.  Replaces the device-side allocation done by
  * HydrostaticFreeSurfaceModel(...) (src/baroclinic_instability_model.jl:67-70). */
@@ -110,20 +124,20 @@ int gb25_clear_error(gb25_handle* h);
 /* State transfer in Oceananigans parent shape.  Replaces sync_states! (src/correctness.jl:92-103)
  * and the Array(parent(ψ)) reads of compare_parent (src/correctness.jl:4-15). */
 int gb25_field_shape(const gb25_handle* h, int field, int shape[3]);
-int gb25_set_field(gb25_handle* h, int field, const float* host_parent);
-int gb25_get_field(gb25_handle* h, int field, float* host_parent);
+int gb25_set_field(gb25_handle* h, int field, const gb25_real* host_parent);
+int gb25_get_field(gb25_handle* h, int field, gb25_real* host_parent);
 /* Interior-shaped transfers: what Oceananigans' set!(model, u=..., v=...) writes and Array(interior(ψ)) reads
  * (correctness/correctness_baroclinic_instability_simulation_run.jl:40-42; src/model_utils.jl:99-131 for T, S).
  * The host array has the interior shape of the field — (Nx, Ny, Nz) for a (C,C,C) field, Ny+1 rows for a Face-y field
  * on a tile that owns the north wall of a Bounded grid, Nz+1 levels for w, one level for 2-D fields — and halos are
  * left untouched.  gb25_interior_shape returns it. */
 int gb25_interior_shape(const gb25_handle* h, int field, int shape[3]);
-int gb25_set_interior(gb25_handle* h, int field, const float* host_interior);
-int gb25_get_interior(gb25_handle* h, int field, float* host_interior);
+int gb25_set_interior(gb25_handle* h, int field, const gb25_real* host_interior);
+int gb25_get_interior(gb25_handle* h, int field, gb25_real* host_interior);
 /* Batched transfers: n fields, all copies enqueued back to back on the handle's stream (one cudaMemcpy3DAsync per
  * field) and ONE synchronisation at the end.  interior = 0: parent shape, 1: interior shape. */
-int gb25_set_fields(gb25_handle* h, int n, const int* fields, const float* const* host, int interior);
-int gb25_get_fields(gb25_handle* h, int n, const int* fields, float* const* host, int interior);
+int gb25_set_fields(gb25_handle* h, int n, const int* fields, const gb25_real* const* host, int interior);
+int gb25_get_fields(gb25_handle* h, int n, const int* fields, gb25_real* const* host, int interior);
 /* model.clock: time, iteration, last_Δt (src/baroclinic_instability_model.jl:82) */
 int gb25_set_clock(gb25_handle* h, double time, long iteration, float last_dt);
 int gb25_get_clock(const gb25_handle* h, double* time, long* iteration, float* last_dt);
@@ -154,7 +168,7 @@ int gb25_compute_boundary_tendencies(gb25_handle* h);/* precompile.jl:52-61  (fl
  * src/baroclinic_instability_model.jl has none, and gb25_compute_boundary_tendencies is then a no-op.  With a flux set,
  * gb25_compute_tendencies / gb25_update_state / the step entry points add G[i,j,1] += J_bottom Az / V and
  * G[i,j,Nz] -= J_top Az / V after the interior tendencies, as Oceananigans' apply_z_bcs! does. */
-int gb25_set_flux_boundary_condition(gb25_handle* h, int field, int side, const float* flux_parent_2d);
+int gb25_set_flux_boundary_condition(gb25_handle* h, int field, int side, const gb25_real* flux_parent_2d);
 int gb25_ab2_step(gb25_handle* h, float dt, float chi); /* precompile.jl:121-123 (incl. split-explicit)    */
 int gb25_correct_velocities_and_cache_previous_tendencies(gb25_handle* h); /* precompile.jl:125-127         */
 

@@ -26,7 +26,7 @@ def main():
 
     argv = [a for a in sys.argv[1:] if a != "--baroclinic-state"]
     parsed = A.parse_baroclinic_instability_args(grid_x_default=1536, grid_y_default=768, grid_z_default=4, argv=argv)
-    A.require_float32(parsed)
+    FT = A.supported_float_type(parsed)          # Float32: all kernel generations; Float64: libgb25cuda_f64.so
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -44,9 +44,9 @@ def main():
     print(f"[{rank}] Generating model (Nx={Nx}, Ny={Ny})...", file=sys.stderr)
     if world > 1:
         model = D.sharded_baroclinic_instability_model(M.B200(local), Nx // Rx, Ny // Ry, Nz, Δt=1.0, Rx=Rx, Ry=Ry,
-                                                       rank=rank, dist=dist, halo=(H, H, H))
+                                                       rank=rank, dist=dist, halo=(H, H, H), float_type=FT)
     else:
-        model = M.baroclinic_instability_model(M.B200(local), Nx, Ny, Nz, Δt=1.0, halo=(H, H, H))
+        model = M.baroclinic_instability_model(M.B200(local), Nx, Ny, Nz, Δt=1.0, halo=(H, H, H), float_type=FT)
     if "--baroclinic-state" in sys.argv:
         M.set_baroclinic_instability(model)
         rng = np.random.default_rng(42 + rank)

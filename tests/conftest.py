@@ -30,7 +30,7 @@ def cuda_lib():
 
 
 def make_models(grid_type, Nx, Ny, Nz, dt, oracle_mod, dtype=np.float32, physics=None, seed=42, with_cuda=True,
-                state="baroclinic"):
+                state="baroclinic", cuda_dtype=np.float32):
     """Build the (cuda, oracle) pair of the reference's correctness protocol
     (/root/reference/correctness/correctness_baroclinic_instability_simulation_run.jl:33-43):
     same model on both architectures, random u, v, state synchronised."""
@@ -43,6 +43,7 @@ def make_models(grid_type, Nx, Ny, Nz, dt, oracle_mod, dtype=np.float32, physics
     M.set(vm, u=1e-3 * rng.random(vm.interior("u").shape), v=1e-3 * rng.random(vm.interior("v").shape))
     rm = None
     if with_cuda:
-        rm = M.baroclinic_instability_model(M.B200(0), Nx, Ny, Nz, Δt=dt, grid_type=grid_type, physics=physics)
+        rm = M.baroclinic_instability_model(M.B200(0), Nx, Ny, Nz, Δt=dt, grid_type=grid_type, physics=physics,
+                                            float_type=cuda_dtype)
         M.sync_states(rm, vm)
     return rm, vm

@@ -29,7 +29,12 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     for name in declared:
         assert hasattr(cuda_lib, name), f"{name} declared in gb25cuda.h but not exported"
     assert sorted(L.EXPORTED_SYMBOLS) == declared
-    assert cuda_lib.gb25_abi_version() == 1
+    assert cuda_lib.gb25_abi_version() == 1 and cuda_lib.gb25_real_bytes() == 4
+    # the Float64 build of the same sources exports the same interface
+    f64 = L.load(np.float64)
+    for name in declared:
+        assert hasattr(f64, name), f"{name} missing from libgb25cuda_f64.so"
+    assert f64.gb25_real_bytes() == 8
 
 
 def test_signatures_carry_no_torch_or_cxx_types():

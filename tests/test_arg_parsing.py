@@ -12,7 +12,7 @@ def test_defaults_and_keys_follow_the_reference():
     d = A.parse_baroclinic_instability_args(grid_x_default=1, grid_y_default=1, grid_z_default=1,
                                             argv=["--grid-x", "192", "--grid-y", "96", "--grid-z", "50", "--float-type", "f32"])
     assert (d["grid-x"], d["grid-y"], d["grid-z"]) == (192, 96, 50)
-    assert A.float_type_from_args(d) is np.float32 and A.require_float32(d) is np.float32
+    assert A.float_type_from_args(d) is np.float32 and A.supported_float_type(d) is np.float32
     assert A.multifloat_from_args(d) is None
 
 
@@ -26,10 +26,12 @@ def test_float_type_strings():
         A.float_type_to_string(int)
 
 
-def test_only_float32_is_built():
+def test_float32_and_float64_are_built():
     d = A.parse_baroclinic_instability_args(grid_x_default=8, grid_y_default=8, grid_z_default=2, argv=[])
-    with pytest.raises(ValueError, match="Float32"):
-        A.require_float32(d)                      # the reference's default, Float64, is refused loudly
+    assert A.supported_float_type(d) is np.float64      # the reference's default
+    d["float-type"] = "f16"
+    with pytest.raises(ValueError, match="Float32 and Float64"):
+        A.supported_float_type(d)
     d["target-float-type"] = "f32"
     with pytest.raises(NotImplementedError):
         A.multifloat_from_args(d)
