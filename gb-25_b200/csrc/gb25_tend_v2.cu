@@ -11,6 +11,8 @@
 //   * upwinding is branch-free (select the mirrored window, then one WENO evaluation),
 //   * cells whose stencil is not clear of bathymetry / walls (k-1 <= knear) fall back to the generic
 //     per-cell function, so the fast path carries no masks and no order reduction in x and y.
+#include <cstdlib>
+
 #include "gb25_internal.h"
 #include "gb25_tend_generic.cuh"
 
@@ -241,11 +243,118 @@ __global__ void __launch_bounds__(128, AUX_MINB) k_aux_columns(DevGrid g, const 
     zeta[q3] = (d1 - d2) / azff;
   }
 }
+// The same pass with NC = 2 or 4 x-adjacent columns per thread and 64- / 128-bit accesses: one thread per aligned group of
+// storage columns (the whole parent width; the outermost ring is computed with clamped neighbours and NOT stored, as the
+// scalar kernel leaves it untouched).  Per level and group: 4 vector loads + 2 scalar loads and 4 vector stores instead of
+// 6 NC scalar loads and 4 NC scalar stores — the pass is bound by memory latency (ncu: long-scoreboard 18 stalls per issue,
+// 3.6 TB/s), and a thread now keeps NC times the bytes in flight.  Same expressions per column, bit-identical results.
+template <int NC> struct VecT;
+template <> struct VecT<2> { typedef float2 T; };
+template <> struct VecT<4> { typedef float4 T; };
+template <int NC> __device__ __forceinline__ void ldvec(const float* p, float (&o)[NC]) {
+  const typename VecT<NC>::T a = *reinterpret_cast<const typename VecT<NC>::T*>(p);
+  const float* q = reinterpret_cast<const float*>(&a);
+#pragma unroll
+  for (int c = 0; c < NC; c++) o[c] = q[c];
+}
+template <int NC> __device__ __forceinline__ void stvec(float* p, const float (&o)[NC], int lo, int hi) {   // components lo..hi-1 are stored
+  if (lo == 0 && hi == NC) {
+    typename VecT<NC>::T a;
+    float* q = reinterpret_cast<float*>(&a);
+#pragma unroll
+    for (int c = 0; c < NC; c++) q[c] = o[c];
+    *reinterpret_cast<typename VecT<NC>::T*>(p) = a;
+  } else {
+#pragma unroll
+    for (int c = 0; c < NC; c++) if (c >= lo && c < hi) p[c] = o[c];
+  }
+}
+#ifndef AUXV_MINB
+#define AUXV_MINB 4
+#endif
+#ifndef AUXV_UNROLL
+#define AUXV_UNROLL 2
+#endif
+template <int NC>
+__global__ void __launch_bounds__(128, AUXV_MINB) k_aux_columns_vec(DevGrid g, const float* __restrict__ u, const float* __restrict__ v,
+                                                                   float* __restrict__ w, float* __restrict__ zeta, float* __restrict__ dxU,
+                                                                   float* __restrict__ dyV) {
+  const int I0 = NC * (blockIdx.x * blockDim.x + threadIdx.x);    // first storage column of the group
+  const int J = blockIdx.y + 1;                                    // storage row 1 .. PY-3
+  const int PX = g.PX, n2 = g.n2;
+  if (I0 >= PX) return;
+  const int lo = I0 == 0 ? 1 : 0, hi = (I0 + NC == PX) ? NC - 1 : NC;      // the outermost ring is not stored
+  const int j = J - g.Hy + 1;
+  const int q2 = I0 + PX * J;
+  const int qE = min(I0 + NC, PX - 1) + PX * J, qW = max(I0 - 1, 0) + PX * J;   // neighbours of the group (clamped at the ring)
+  float dyf[NC + 1], dxN[NC], dxS[NC], az[NC], zy[NC + 1], zxN[NC], zxS[NC], azff[NC];
+  int t1[NC], t2[NC];
+  bool safe = true;
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    dyf[c] = g.dyfc[q2 + c]; dxN[c] = g.dxcf[q2 + PX + c]; dxS[c] = g.dxcf[q2 + c]; az[c] = g.azcc[q2 + c];
+    zy[c + 1] = g.dycf[q2 + c]; zxN[c] = g.dxfc[q2 + c]; zxS[c] = g.dxfc[q2 - PX + c]; azff[c] = g.azff[q2 + c];
+    safe = safe && az[c] > 1e-10f && az[c] < 1e30f && azff[c] > 1e-10f && azff[c] < 1e30f;
+    t1[c] = -1; t2[c] = -1;
+  }
+  dyf[NC] = g.dyfc[qE]; zy[0] = g.dycf[qW];
+  if (g.immersed && g.cond_diff) {
+    const bool o0 = y_outside(g, j), om = y_outside(g, j - 1);
+    int kc[NC + 1], km[NC + 1];      // kb of columns I0-1 .. I0+NC-1 on rows j and j-1
+    kc[0] = o0 ? GB25_BIG : (int)g.kb[qW]; km[0] = om ? GB25_BIG : (int)g.kb[qW - PX];
+#pragma unroll
+    for (int c = 0; c < NC; c++) { kc[c + 1] = o0 ? GB25_BIG : (int)g.kb[q2 + c]; km[c + 1] = om ? GB25_BIG : (int)g.kb[q2 - PX + c]; }
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      t1[c] = max(min(kc[c + 1], km[c + 1]), min(kc[c], km[c]));
+      t2[c] = max(min(kc[c + 1], kc[c]), min(km[c + 1], km[c]));
+    }
+  }
+  float raz[NC], razff[NC], wk[NC];
+#pragma unroll
+  for (int c = 0; c < NC; c++) { raz[c] = safe ? rcp_refined(az[c]) : 0.f; razff[c] = safe ? rcp_refined(azff[c]) : 0.f; wk[c] = 0.f; }
+  size_t q3 = q2 + (size_t)n2 * g.Hz;  // k = 1
+  stvec<NC>(w + q3, wk, lo, hi);
+  const int oE = qE - q2, oW = qW - q2;
+  constexpr int kUnroll = AUXV_UNROLL;
+#pragma unroll kUnroll
+  for (int k = 1; k <= g.Nz; k++, q3 += n2) {
+    const float dz = g.dzc[k + g.Hz - 1];
+    float uu[NC + 1], vv[NC + 1], vn[NC], us[NC];
+    ldvec<NC>(u + q3, *reinterpret_cast<float(*)[NC]>(uu));
+    ldvec<NC>(v + q3, *reinterpret_cast<float(*)[NC]>(vv + 1));
+    ldvec<NC>(v + q3 + PX, vn);
+    ldvec<NC>(u + q3 - PX, us);
+    uu[NC] = u[q3 + oE]; vv[0] = v[q3 + oW];
+    float dU[NC], dV[NC], zt[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      dU[c] = dyf[c + 1] * dz * uu[c + 1] - dyf[c] * dz * uu[c];
+      dV[c] = dxN[c] * dz * vn[c] - dxS[c] * dz * vv[c + 1];
+      float d1 = zy[c + 1] * vv[c + 1] - zy[c] * vv[c];
+      float d2 = zxN[c] * uu[c] - zxS[c] * us[c];
+      if (k <= t1[c]) d1 = 0.f;
+      if (k <= t2[c]) d2 = 0.f;
+      if (safe) { wk[c] = wk[c] - div_by(dU[c] + dV[c], az[c], raz[c]); zt[c] = div_by(d1 - d2, azff[c], razff[c]); }
+      else { wk[c] = wk[c] - (dU[c] + dV[c]) / az[c]; zt[c] = (d1 - d2) / azff[c]; }
+    }
+    stvec<NC>(dxU + q3, dU, lo, hi); stvec<NC>(dyV + q3, dV, lo, hi);
+    stvec<NC>(w + q3 + n2, wk, lo, hi); stvec<NC>(zeta + q3, zt, lo, hi);
+  }
+}
 void launch_aux_columns(Handle* h) {
   const DevGrid& g = h->g;
   const int nx = g.Nx + 2 * g.Hx - 2, ny = g.Ny + 2 * g.Hy - 2;
-  dim3 b(128), gr((nx + 127) / 128, ny);
   StageScope ts(h, "kernel:k_aux_columns");
+  static const int nc = []() { const char* e = getenv("GB25_AUX_NC"); return e ? atoi(e) : 4; }();
+  if ((nc == 4 || nc == 2) && g.PX % 4 == 0) {
+    dim3 b(128), gr((g.PX / nc + 127) / 128, ny);
+    if (nc == 4) k_aux_columns_vec<4><<<gr, b, 0, h->stream>>>(g, h->f.u, h->f.v, h->f.w, h->zeta, h->dxU, h->dyV);
+    else k_aux_columns_vec<2><<<gr, b, 0, h->stream>>>(g, h->f.u, h->f.v, h->f.w, h->zeta, h->dxU, h->dyV);
+    h->count_launch();
+    return;
+  }
+  dim3 b(128), gr((nx + 127) / 128, ny);
   k_aux_columns<<<gr, b, 0, h->stream>>>(g, h->f.u, h->f.v, h->f.w, h->zeta, h->dxU, h->dyV);
   h->count_launch();
 }
