@@ -330,6 +330,8 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
     h->use_tma = !(t && t[0] == '0');
     const char* sp = getenv("GB25_SPECULATE");
     h->use_spec = !(sp && sp[0] == '0');
+    const char* ov = getenv("GB25_OVERLAP");
+    h->use_overlap = !(ov && ov[0] == '0');
     const char* zf = getenv("GB25_ZHALO_FOLD");
     h->use_zfold = !(zf && zf[0] == '0');
     const char* pk = getenv("GB25_PACKED");
@@ -471,14 +473,47 @@ static void fill_prognostic(Handle* h) {
 // those halos in between (the substep kernels take GU,GV at interior points and start from the halos of the previous
 // step's fill), and the later fill overwrites every halo cell of the earlier ones, so the state after the step is the same —
 // with one exchange sequence between tiles instead of four.
-static void fill_prognostic_fused(Handle* h, bool zdone_uv, bool zdone_ts) {
+static void fill_prognostic_fused(Handle* h, bool zdone_uv, bool zdone_ts, bool ts_done) {
   StageScope t(h, "fill_halo_regions");
   DevFields& f = h->f;
   const int zu = zdone_uv ? 1 : 0, zv = zdone_uv ? 2 : 0, zt = zdone_ts ? 1 : 0;
+  if (ts_done) {     // T, S were filled ahead of the barotropic solve (fill_tracers_early)
+    HaloSpec s[7] = {{f.u, 1, 0, 0, -1.f, 0, zu}, {f.v, 0, 1, 0, -1.f, 0, zv},
+                     {f.eta, 0, 0, 1, 1.f, 1}, {f.bu, 1, 0, 0, -1.f, 1}, {f.bv, 0, 1, 0, -1.f, 1},
+                     {f.gU, 1, 0, 0, -1.f, 1}, {f.gV, 0, 1, 0, -1.f, 1}};
+    launch_fill_halo(h, s, 7, true);
+    return;
+  }
   HaloSpec s[9] = {{f.u, 1, 0, 0, -1.f, 0, zu}, {f.v, 0, 1, 0, -1.f, 0, zv}, {f.T, 0, 0, 0, 1.f, 0, zt}, {f.S, 0, 0, 0, 1.f, 0, zt},
                    {f.eta, 0, 0, 1, 1.f, 1}, {f.bu, 1, 0, 0, -1.f, 1}, {f.bv, 0, 1, 0, -1.f, 1},
                    {f.gU, 1, 0, 0, -1.f, 1}, {f.gV, 0, 1, 0, -1.f, 1}};
   launch_fill_halo(h, s, 9, true);
+}
+struct StreamSwap {   // launch on another stream for the lifetime of the object
+  Handle* h; cudaStream_t saved;
+  StreamSwap(Handle* h_, cudaStream_t s) : h(h_), saved(h_->stream) { h->stream = s; }
+  ~StreamSwap() { h->stream = saved; }
+};
+// T and S are final the moment the AB2 epilogue of the previous step has written them (masked, z halos included): their
+// horizontal halo fill / tile exchange and the hydrostatic pressure scan depend on nothing the barotropic solve or the
+// corrector produce, so they run on the second stream underneath those two stages.  Between tiles this is the second lane
+// of the exchange (own sequence numbers, flag words and inbox slots), so that the strips of T and S cross NVLink while the
+// persistent substep kernel is latency-bound, and the exchange on the critical path carries two 3-D fields instead of four.
+static void fill_tracers_early(Handle* h, bool zdone_ts) {
+  DevFields& f = h->f;
+  cudaEventRecord(h->ev_fork, h->stream);
+  cudaStreamWaitEvent(h->stream2, h->ev_fork, 0);
+  StreamSwap sw(h, h->stream2);
+  h->ex.lane = 1;
+  {
+    StageScope t(h, "fill_halo_regions_TS");
+    const int zt = zdone_ts ? 1 : 0;
+    HaloSpec s3[2] = {{f.T, 0, 0, 0, 1.f, 0, zt}, {f.S, 0, 0, 0, 1.f, 0, zt}};
+    launch_fill_halo(h, s3, 2, true);
+  }
+  h->ex.lane = 0;
+  { StageScope t(h, "update_hydrostatic_pressure"); launch_compute_p(h); }
+  cudaEventRecord(h->ev_join, h->stream2);
 }
 static void stage_mask(Handle* h) { StageScope t(h, "mask_immersed_fields"); launch_mask(h, false); }
 static void stage_aux(Handle* h) {
@@ -529,9 +564,10 @@ static void swap_state_buffers(Handle* h) {
 // fused step path: identical results, fewer passes over the 3-D state (see gb25_kernels.cu "Fused step path")
 static void one_time_step_fused(Handle* h, float dt, float chi) {
   DevFields& f = h->f;
-  bool zdone_ts = false;
+  bool zdone_ts = false, ts_early = false;
   if (h->spec.valid && h->spec.dt == dt && h->spec.chi == chi) {
     zdone_ts = h->spec.zhalo;
+    ts_early = h->use_overlap && h->cfg.closure != 2;
     // the tendency kernels of the previous step already wrote u*, v*, T', S' (masked) into the other state buffers and
     // GU, GV, sum dz u*, sum dz v* into their 2-D arrays: the AB2 stage is a pointer swap
     StageScope t(h, "ab2_step_fields");
@@ -541,6 +577,7 @@ static void one_time_step_fused(Handle* h, float dt, float chi) {
     StageScope t(h, "ab2_step_fields"); launch_ab2_fused(h, dt, chi);
   }
   h->spec.valid = false;
+  if (ts_early) fill_tracers_early(h, zdone_ts);
   if (h->cfg.closure == 2) { StageScope t(h, "vertical_diffusion"); launch_implicit_columns(h, dt, true); }
   { StageScope t(h, "split_explicit_free_surface"); launch_barotropic(h, dt); }
   h->time += (double)dt; h->iteration += 1; h->last_dt = dt;
@@ -552,8 +589,13 @@ static void one_time_step_fused(Handle* h, float dt, float chi) {
     std::swap(f.gn[q], f.gm[q]);
     std::swap(h->field_ptr[GB25_GN_U + q], h->field_ptr[GB25_GM_U + q]);
   }
-  fill_prognostic_fused(h, zdone_uv, zdone_ts && h->cfg.closure != 2);   // (the implicit solve rewrites T, S after the epilogue)
-  stage_aux(h);
+  fill_prognostic_fused(h, zdone_uv, zdone_ts && h->cfg.closure != 2, ts_early);   // (the implicit solve rewrites T, S after the epilogue)
+  if (ts_early) {
+    { StageScope t(h, "compute_w_from_continuity"); launch_aux_columns(h); }
+    cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+  } else {
+    stage_aux(h);
+  }
   if (spec_possible(h)) {
     const Ab2Spec sp = {dt, 1.5f + h->cfg.chi, 0.5f + h->cfg.chi, (h->use_zfold && h->g.Nz >= h->g.Hz) ? 1 : 0};
     stage_tend(h, &sp);

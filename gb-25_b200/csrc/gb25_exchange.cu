@@ -60,17 +60,17 @@ __global__ void k_push_cols(DevGrid g, PushBatch pb, int scol, int dcol, int nco
 // line into the neighbour's column inbox; after the handshake the receiver scatters its inbox into its own halo columns
 // (a local copy).  The inbox has two halves, used alternately by sequence parity: a neighbour that runs ahead may already
 // push the strips of the NEXT fill while this tile has not unpacked the current one.
-__global__ void k_push_cols_packed(DevGrid g, PushBatch pb, int scol, int three_d, real* __restrict__ box) {
+__global__ void k_push_cols_packed(DevGrid g, PushBatch pb, int scol, int three_d, real* __restrict__ box, int slot0) {
   const int c = threadIdx.x;                                  // 0 .. Hx-1
   const int J = blockIdx.x * blockDim.y + threadIdx.y;        // storage row
   if (c >= g.Hx || J >= g.PY) return;
   const PushField pf = pb.f[blockIdx.z];
   if (pf.flat) { if (blockIdx.y > 0) return; three_d = 0; }
   const size_t po = (three_d ? (size_t)g.n2 * blockIdx.y : 0) + (size_t)g.PX * J;
-  box[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * g.PY + J) * g.Hx + c] = pf.src[po + scol + c];
+  box[(((size_t)(blockIdx.z + slot0) * gridDim.y + blockIdx.y) * g.PY + J) * g.Hx + c] = pf.src[po + scol + c];
 }
 // blockIdx.z = 2 * field slot + direction (0: from the west tile -> columns [0, Hx), 1: from the east tile -> [Nx+Hx, PX))
-__global__ void k_unpack_cols(DevGrid g, PushBatch pb, int three_d, const real* __restrict__ box_w, const real* __restrict__ box_e) {
+__global__ void k_unpack_cols(DevGrid g, PushBatch pb, int three_d, const real* __restrict__ box_w, const real* __restrict__ box_e, int slot0) {
   const int c = threadIdx.x;
   const int J = blockIdx.x * blockDim.y + threadIdx.y;
   if (c >= g.Hx || J >= g.PY) return;
@@ -79,7 +79,7 @@ __global__ void k_unpack_cols(DevGrid g, PushBatch pb, int three_d, const real* 
   if (pf.flat) { if (blockIdx.y > 0) return; three_d = 0; }
   const size_t po = (three_d ? (size_t)g.n2 * blockIdx.y : 0) + (size_t)g.PX * J;
   const real* box = dir ? box_e : box_w;
-  pf.dst[po + (dir ? g.Nx + g.Hx : 0) + c] = box[(((size_t)q * gridDim.y + blockIdx.y) * g.PY + J) * g.Hx + c];
+  pf.dst[po + (dir ? g.Nx + g.Hx : 0) + c] = box[(((size_t)(q + slot0) * gridDim.y + blockIdx.y) * g.PY + J) * g.Hx + c];
 }
 // tripolar fold: my top rows -> the partner's north halo rows, x-mirrored, sign-flipped for vectors.
 // `second` selects the Face-x column whose partner lives one tile further (see the header comment of
@@ -173,15 +173,15 @@ static void signal_slots(Handle* h, int slot_mask) {
   Exchange& X = h->ex;
   SignalSet s; s.n = 0;
   for (int sl = 0; sl < EX_NSLOT; sl++)
-    if (((slot_mask >> sl) & 1) && X.to[sl].rank >= 0 && X.to[sl].rank != X.rank) s.dst[s.n++] = X.to[sl].flags + kOpposite[sl];
+    if (((slot_mask >> sl) & 1) && X.to[sl].rank >= 0 && X.to[sl].rank != X.rank) s.dst[s.n++] = X.to[sl].flags + EX_LANE_FLAGS * X.lane + kOpposite[sl];
   if (!s.n) return;
   if (memops_available()) {
     bool ok = true;
-    for (int q = 0; q < s.n; q++) ok &= g_write32((CUstream)h->stream, (CUdeviceptr)s.dst[q], (cuuint32_t)X.seq, CU_STREAM_WRITE_VALUE_DEFAULT) == CUDA_SUCCESS;
+    for (int q = 0; q < s.n; q++) ok &= g_write32((CUstream)h->stream, (CUdeviceptr)s.dst[q], (cuuint32_t)X.seqs[X.lane], CU_STREAM_WRITE_VALUE_DEFAULT) == CUDA_SUCCESS;
     if (ok) return;
     g_memops = 0;   // (not supported on this address / driver: use the kernels from now on)
   }
-  k_signal<<<1, 32, 0, h->stream>>>(s, X.seq); h->count_launch();
+  k_signal<<<1, 32, 0, h->stream>>>(s, X.seqs[X.lane]); h->count_launch();
 }
 static void wait_slots(Handle* h, int slot_mask) {
   Exchange& X = h->ex;
@@ -192,11 +192,11 @@ static void wait_slots(Handle* h, int slot_mask) {
   if (memops_available()) {
     bool ok = true;
     for (int sl = 0; sl < EX_NSLOT; sl++)
-      if ((m >> sl) & 1) ok &= g_wait32((CUstream)h->stream, (CUdeviceptr)(X.flags + sl), (cuuint32_t)X.seq, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS;
+      if ((m >> sl) & 1) ok &= g_wait32((CUstream)h->stream, (CUdeviceptr)(X.flags + EX_LANE_FLAGS * X.lane + sl), (cuuint32_t)X.seqs[X.lane], CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS;
     if (ok) return;
     g_memops = 0;
   }
-  k_wait<<<1, 32, 0, h->stream>>>(X.flags, m, X.seq); h->count_launch();
+  k_wait<<<1, 32, 0, h->stream>>>(X.flags + EX_LANE_FLAGS * X.lane, m, X.seqs[X.lane]); h->count_launch();
 }
 
 void launch_fill_halo_dist(Handle* h, const HaloSpec* specs, int n, bool three_d) {
@@ -239,23 +239,26 @@ void launch_fill_halo_dist(Handle* h, const HaloSpec* specs, int n, bool three_d
     mask_y |= (1 << SLOT_FOLD) | (1 << SLOT_FOLD2);
   }
   delete tsy;
-  if (mask_y) { StageScope ts(h, "exchange:handshake_y"); X.seq++; signal_slots(h, mask_y); wait_slots(h, mask_y); }
+  if (mask_y) { StageScope ts(h, "exchange:handshake_y"); X.seqs[X.lane]++; signal_slots(h, mask_y); wait_slots(h, mask_y); }
   // ---- phase X: west / east strips over the full parent extent (carries the y and z halos into the corners)
   if (c.Rx == 1) { launch_halo_periodic_x(h, specs, n, three_d); return; }
   {
     dim3 bc(g.Hx, 32), gc((g.PY + 31) / 32, np, 0);
-    X.seq++;
-    X.xseq++;     // (the parity of the column phases, not of all phases: a fill with a row phase advances seq twice)
-    real* const mybox = X.xbox + (size_t)(X.xseq & 1) * 2 * X.xbox_stride;
+    // the second lane (T, S ahead of the barotropic solve, on the second stream) has its own sequence numbers and flag words
+    // and uses field slots 7, 8 of the column inbox; the first lane then carries at most seven fields (slots 0 .. 6)
+    const int slot0 = X.lane ? 7 : 0;
+    X.seqs[X.lane]++;
+    X.xseqs[X.lane]++;     // (the parity of the column phases, not of all phases: a fill with a row phase advances seq twice)
+    real* const mybox = X.xbox + (size_t)(X.xseqs[X.lane] & 1) * 2 * X.xbox_stride;
     {
       StageScope ts(h, "exchange:push_x");
-      const size_t off = (size_t)(X.xseq & 1) * 2 * X.xbox_stride;
+      const size_t off = (size_t)(X.xseqs[X.lane] & 1) * 2 * X.xbox_stride;
       PushBatch pe = make_push(h, specs, n, SLOT_E);   // my last Hx interior columns -> the east tile's inbox "from the west"
       gc.z = pe.n;
-      if (pe.n) { k_push_cols_packed<<<gc, bc, 0, h->stream>>>(g, pe, g.Nx, three_d, X.to[SLOT_E].fld[EX_XBOX] + off); h->count_launch(); }
+      if (pe.n) { k_push_cols_packed<<<gc, bc, 0, h->stream>>>(g, pe, g.Nx, three_d, X.to[SLOT_E].fld[EX_XBOX] + off, slot0); h->count_launch(); }
       PushBatch pw = make_push(h, specs, n, SLOT_W);   // my first Hx interior columns -> the west tile's inbox "from the east"
       gc.z = pw.n;
-      if (pw.n) { k_push_cols_packed<<<gc, bc, 0, h->stream>>>(g, pw, g.Hx, three_d, X.to[SLOT_W].fld[EX_XBOX] + off + X.xbox_stride); h->count_launch(); }
+      if (pw.n) { k_push_cols_packed<<<gc, bc, 0, h->stream>>>(g, pw, g.Hx, three_d, X.to[SLOT_W].fld[EX_XBOX] + off + X.xbox_stride, slot0); h->count_launch(); }
     }
     {
       StageScope ts(h, "exchange:handshake_x");
@@ -268,7 +271,7 @@ void launch_fill_halo_dist(Handle* h, const HaloSpec* specs, int n, bool three_d
       for (int q = 0; q < n; q++)
         if (ex_field_id(h, specs[q].a) >= 0) pu.f[pu.n++] = PushField{nullptr, specs[q].a, specs[q].lx, specs[q].ly, specs[q].lz, specs[q].sign, specs[q].flat};
       gc.z = 2 * pu.n;
-      if (pu.n) { k_unpack_cols<<<gc, bc, 0, h->stream>>>(g, pu, three_d, mybox, mybox + X.xbox_stride); h->count_launch(); }
+      if (pu.n) { k_unpack_cols<<<gc, bc, 0, h->stream>>>(g, pu, three_d, mybox, mybox + X.xbox_stride, slot0); h->count_launch(); }
     }
   }
 }
@@ -286,7 +289,7 @@ void exchange_baro_eta(Handle* h) {   // after the eta kernel: the U,V kernel re
   // k_baro_eta(m+1) (just finished) had to read with the substep-m value.  The partner is not my x neighbour when
   // Rx >= 4, so without this handshake nothing orders its next store after my read.
   if (c.topo_y == GB25_TOPO_FOLD && c.ry == c.Ry - 1 && c.Rx > 1) { mask_out |= 1 << SLOT_FOLD; mask_in |= 1 << SLOT_FOLD; }
-  if (mask_out | mask_in) { X.seq++; signal_slots(h, mask_out); wait_slots(h, mask_in); }
+  if (mask_out | mask_in) { X.seqs[X.lane]++; signal_slots(h, mask_out); wait_slots(h, mask_in); }
 }
 void exchange_baro_uv(Handle* h) {    // after the U,V kernel: the eta kernel reads U(i+1), V(j+1)
   Exchange& X = h->ex;
@@ -296,7 +299,7 @@ void exchange_baro_uv(Handle* h) {    // after the U,V kernel: the eta kernel re
   if (c.ry > 0) mask_out |= 1 << SLOT_S;
   if (c.ry < c.Ry - 1) mask_in |= 1 << SLOT_N;
   if (c.topo_y == GB25_TOPO_FOLD && c.ry == c.Ry - 1 && c.Rx > 1) { mask_out |= 1 << SLOT_FOLD; mask_in |= 1 << SLOT_FOLD; }
-  if (mask_out | mask_in) { X.seq++; signal_slots(h, mask_out); wait_slots(h, mask_in); }
+  if (mask_out | mask_in) { X.seqs[X.lane]++; signal_slots(h, mask_out); wait_slots(h, mask_in); }
 }
 
 // --------------------------------------------------------------------------------- C ABI
@@ -335,7 +338,7 @@ static int exchange_finish_connect(Handle* h) {
   // session (a stale number would satisfy a wait).  The caller synchronises all ranks before reconnecting and puts a
   // barrier after it (distributed.connect), so no neighbour writes into this buffer while it is cleared.
   if (cudaMemset(X.flags, 0, 2 << 20) != cudaSuccess) { h->err = "exchange connect: cudaMemset flags"; return GB25_ERR_CUDA; }
-  X.seq = 0; X.xseq = 0;
+  X.seqs[0] = X.seqs[1] = 0; X.xseqs[0] = X.xseqs[1] = 0; X.lane = 0;
   X.on = true;
   baro_plan_free(h);   // the persistent substep kernel restarts its sequence numbers on the (zeroed) shared flag buffer
   return GB25_OK;

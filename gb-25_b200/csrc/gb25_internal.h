@@ -18,6 +18,7 @@ struct HaloSpec { real* a; int lx, ly, lz; real sign; int flat; int zdone; };
 // EX_XBOX: the column inbox (west / east strips arrive packed, see k_push_cols_packed)
 enum ExField { EX_U = 0, EX_V, EX_T, EX_S, EX_ETA, EX_BU, EX_BV, EX_GU, EX_GV, EX_U2, EX_V2, EX_T2, EX_S2, EX_XBOX, EX_NF };
 enum ExSlot { SLOT_W = 0, SLOT_E, SLOT_S, SLOT_N, SLOT_FOLD, SLOT_FOLD2, EX_NSLOT };
+#define EX_LANE_FLAGS 16   // flag words of lane 1 start here (lane 0: words 0 .. EX_NSLOT-1, time-out word EX_NSLOT)
 struct ExPeer { real* fld[EX_NF]; int* flags; int rank; };
 struct Exchange {
   bool on = false;
@@ -27,7 +28,8 @@ struct Exchange {
   size_t xbox_stride = 0;        // floats per (parity, direction) box
   ExPeer to[EX_NSLOT];           // the tile lying in that direction (destination of my pushes); rank < 0: none
   int from_mask_y = 0, from_mask_x = 0, from_mask_fold = 0;   // slots I receive on in each phase
-  int seq = 0, xseq = 0;
+  int seqs[2] = {0, 0}, xseqs[2] = {0, 0};   // sequence numbers per lane (all phases / column phases)
+  int lane = 0;                              // 0: the step's main exchange; 1: the early T, S exchange on the second stream
   std::vector<void*> opened;     // pointers returned by cudaIpcOpenMemHandle
 };
 
@@ -64,6 +66,7 @@ struct gb25_handle {
   real* spec2d[4] = {nullptr, nullptr, nullptr, nullptr};   // speculative GU, GV, sum dz u*, sum dz v* (committed by launch_commit_spec)
   struct { bool valid = false; float dt = 0.f, chi = 0.f; bool zhalo = false; } spec;
   bool use_spec = true;
+  bool use_overlap = true;             // T, S halo fill / exchange + pressure scan on the second stream, under the substeps
   bool use_zfold = true;               // corrector / tracer epilogue also write the z halos of the fields they produce
   // flux boundary conditions (row A7): 2-D device arrays [u, v, T, S][bottom, top], nullptr = no-flux
   real* bflux[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
