@@ -71,11 +71,53 @@ static void parent_shape(const Handle* h, int field, int shape[3]) {
   shape[2] = fi.three_d ? c.Nz + 2 * c.Hz + fi.lz : 1;
 }
 
+// Every allocation gb25_create makes goes through here.  With GB25_GUARD=1 (debug aid; compute-sanitizer is closed on the
+// shared pool) the array sits between two 64 KiB guard zones filled with a byte pattern, and gb25_check_guards counts the
+// guard bytes a kernel has overwritten: an out-of-bounds store within 64 KiB of any array is caught, at full speed, on every
+// kernel generation.  Guarded allocations cannot be exported to other processes (IPC handles map whole allocations).
+#define GB25_GUARD_BYTES ((size_t)64 << 10)
+#define GB25_GUARD_BYTE 0xA5
+static cudaError_t galloc(Handle* h, void** out, size_t bytes) {
+  if (!h->guard) {
+    const cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaSuccess) h->allocs.push_back(*out);
+    return e;
+  }
+  char* base = nullptr;
+  const size_t rounded = (bytes + 255) & ~(size_t)255;
+  const cudaError_t e = cudaMalloc(&base, rounded + 2 * GB25_GUARD_BYTES);
+  if (e != cudaSuccess) return e;
+  cudaMemset(base, GB25_GUARD_BYTE, rounded + 2 * GB25_GUARD_BYTES);
+  cudaMemset(base + GB25_GUARD_BYTES, 0, bytes);
+  h->allocs.push_back(base);
+  h->guards.push_back({base, GB25_GUARD_BYTES + bytes, rounded - bytes + GB25_GUARD_BYTES});
+  *out = base + GB25_GUARD_BYTES;
+  return cudaSuccess;
+}
+extern "C" int gb25_check_guards(gb25_handle* h, long* corrupted_bytes) {
+  REQUIRE(h);
+  if (!corrupted_bytes) return GB25_ERR_INVALID;
+  if (!h->guard) { h->err = "gb25_check_guards: the handle was not created with GB25_GUARD=1"; return GB25_ERR_INVALID; }
+  CK(h, cudaStreamSynchronize(h->stream));
+  std::vector<unsigned char> buf;
+  long bad = 0;
+  for (const auto& gz : h->guards) {
+    const char* zone[2] = {gz.base, gz.base + gz.lo_end};
+    const size_t len[2] = {GB25_GUARD_BYTES, gz.hi_len};
+    for (int z = 0; z < 2; z++) {
+      buf.resize(len[z]);
+      CK(h, cudaMemcpy(buf.data(), zone[z], len[z], cudaMemcpyDeviceToHost));
+      for (unsigned char b : buf) bad += b != GB25_GUARD_BYTE;
+    }
+  }
+  *corrupted_bytes = bad;
+  return GB25_OK;
+}
+
 template <class T>
 static int upload(Handle* h, const T* host, size_t n, const T** out) {
   T* d = nullptr;
-  CK(h, cudaMalloc(&d, n * sizeof(T)));
-  h->allocs.push_back(d);
+  CK(h, galloc(h, (void**)&d, n * sizeof(T)));
   CK(h, cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
   *out = d;
   return GB25_OK;
@@ -242,6 +284,7 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
   }
   Handle* h = new Handle();
   h->timers.reserve(64);
+  { const char* gd = getenv("GB25_GUARD"); h->guard = gd && gd[0] == '1'; }
   h->cfg = *cfg;
   if (cfg->device >= 0) h->device = cfg->device; else cudaGetDevice(&h->device);
   if ((e = cudaSetDevice(h->device)) != cudaSuccess) {
@@ -293,31 +336,27 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
   for (int fidx = 0; fidx < GB25_FIELD_COUNT; fidx++) {
     const size_t n = kFieldInfo[fidx].three_d ? n3 : n2;
     real* d = nullptr;
-    cudaError_t ce = cudaMalloc(&d, n * sizeof(real));
+    cudaError_t ce = galloc(h, (void**)&d, n * sizeof(real));
     if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc field: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
-    h->allocs.push_back(d);
     CKC(ckcuda(cudaMemsetAsync(d, 0, n * sizeof(real), h->stream), "cudaMemset"));
     h->field_ptr[fidx] = d;
   }
   for (int q = 0; q < 4; q++) {
     static const int ids[4] = {GB25_U, GB25_V, GB25_T, GB25_S};
     h->state_buf[0][q] = h->field_ptr[ids[q]];
-    cudaError_t ce = cudaMalloc(&h->state_buf[1][q], n3 * sizeof(real));
+    cudaError_t ce = galloc(h, (void**)&h->state_buf[1][q], n3 * sizeof(real));
     if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc state buffer: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
-    h->allocs.push_back(h->state_buf[1][q]);
     CKC(ckcuda(cudaMemsetAsync(h->state_buf[1][q], 0, n3 * sizeof(real), h->stream), "cudaMemset"));
   }
   for (real** sp : {&h->zeta, &h->dxU, &h->dyV}) {
-    cudaError_t ce = cudaMalloc(sp, n3 * sizeof(real));
+    cudaError_t ce = galloc(h, (void**)sp, n3 * sizeof(real));
     if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc scratch: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
-    h->allocs.push_back(*sp);
     CKC(ckcuda(cudaMemsetAsync(*sp, 0, n3 * sizeof(real), h->stream), "cudaMemset"));
   }
   for (real** sp : {&h->us2, &h->vs2, &h->corr_u, &h->corr_v, &h->carry[0], &h->carry[1], &h->carry[2], &h->carry[3],
                      &h->spec2d[0], &h->spec2d[1], &h->spec2d[2], &h->spec2d[3]}) {
-    cudaError_t ce = cudaMalloc(sp, n2 * sizeof(real));
+    cudaError_t ce = galloc(h, (void**)sp, n2 * sizeof(real));
     if (ce != cudaSuccess) { g_create_error = std::string("gb25_create: cudaMalloc scratch: ") + cudaGetErrorString(ce); gb25_destroy(h); return GB25_ERR_ALLOC; }
-    h->allocs.push_back(*sp);
     CKC(ckcuda(cudaMemsetAsync(*sp, 0, n2 * sizeof(real), h->stream), "cudaMemset"));
   }
   {
@@ -676,8 +715,7 @@ extern "C" int gb25_set_flux_boundary_condition(gb25_handle* h, int field, int s
     int s[3];
     parent_shape(h, field == GB25_V ? GB25_BARO_V : (field == GB25_U ? GB25_BARO_U : GB25_ETA), s);   // 2-D parent of that staggering
     real* d = nullptr;
-    CK(h, cudaMalloc(&d, (size_t)h->g.n2 * sizeof(real)));
-    h->allocs.push_back(d);
+    CK(h, galloc(h, (void**)&d, (size_t)h->g.n2 * sizeof(real)));
     CK(h, cudaMemset(d, 0, (size_t)h->g.n2 * sizeof(real)));
     CK(h, cudaMemcpy2D(d, (size_t)h->g.PX * sizeof(real), flux, (size_t)s[0] * sizeof(real), (size_t)s[0] * sizeof(real), s[1], cudaMemcpyHostToDevice));
     h->bflux[q][side] = d;

@@ -346,6 +346,7 @@ static int exchange_finish_connect(Handle* h) {
 
 extern "C" int gb25_exchange_export(gb25_handle* h, void* blob) {
   if (!h || !blob) return GB25_ERR_INVALID;
+  if (h->guard) { h->err = "gb25_exchange_export: guarded allocations (GB25_GUARD=1) cannot be exported"; return GB25_ERR_INVALID; }
   cudaSetDevice(h->device);
   ExBlob b; memset(&b, 0, sizeof b);
   Exchange& X = h->ex;

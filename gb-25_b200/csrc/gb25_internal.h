@@ -50,6 +50,10 @@ struct gb25_handle {
   int device = 0;
   std::vector<float> weights;
   std::vector<void*> allocs;
+  // GB25_GUARD=1: every allocation of gb25_create sits between two guard zones (gb25_check_guards)
+  bool guard = false;
+  struct GuardZone { char* base; size_t lo_end, hi_len; };   // zones: [base, base + 64 KiB) and [base + lo_end, base + lo_end + hi_len)
+  std::vector<GuardZone> guards;
   real* field_ptr[GB25_FIELD_COUNT];
   // scratch 3-D arrays shared by the v2 kernels: vorticity (F,F,C), delta_x(Ax u) and delta_y(Ay v) at (C,C,C)
   real *zeta = nullptr, *dxU = nullptr, *dyV = nullptr;

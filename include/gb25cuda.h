@@ -180,6 +180,10 @@ int gb25_kernel_launch_count(const gb25_handle* h, long* launches);
 int gb25_enable_stage_timers(gb25_handle* h, int enable);
 int gb25_get_stage_times(gb25_handle* h, const char** names, float* ms, long* calls, int cap);
 
+/* Debug aid: a handle created while the environment holds GB25_GUARD=1 places every device array between two 64 KiB
+ * guard zones; gb25_check_guards counts the guard bytes that kernels have overwritten since (0 = no out-of-bounds store). */
+int gb25_check_guards(gb25_handle* h, long* corrupted_bytes);
+
 /* Multi-GPU (one process per GPU).  Neighbour tiles exchange halos over NVLink through peer-mapped
  * memory: every rank exports its exchange window (gb25_exchange_export), the host side gathers the
  * opaque blobs from all ranks (any transport: torch.distributed, MPI, a file) and hands the full set

@@ -502,6 +502,42 @@ def test_float64_build_against_float64_oracle(oracle_mod, grid_type, Nx, Ny, Nz,
     rm.close()
 
 
+@pytest.mark.parametrize("grid_type,Nx,Ny,Nz", GRIDS + [("gaussian_islands", 64, 51, 9), ("simple_lat_lon", 96, 45, 9),
+                                                        ("gaussian_islands", 256, 96, 12), ("simple_lat_lon", 130, 33, 7)])
+@pytest.mark.parametrize("variant", ["default", "GB25_FUSED=0", "GB25_TMA=0", "GB25_PACKED=0", "GB25_TMA_TRACER=0",
+                                     "GB25_BARO_PERSISTENT=0", "GB25_SPECULATE=0", "GB25_OVERLAP=0", "closure=1", "closure=2"])
+def test_no_out_of_bounds_stores_under_guard_zones(monkeypatch, grid_type, Nx, Ny, Nz, variant):
+    """compute-sanitizer is closed on the shared pool, so the library carries its own store checker: with GB25_GUARD=1 every
+    device array sits between two 64 KiB guard zones, and after stepping through every kernel generation — fused and
+    operator path, TMA / register-blocked / per-cell tendencies, persistent and per-substep barotropic kernels, with and
+    without the AB2 epilogue and the second stream, both closures, sizes with partial tiles — not one guard byte may have
+    changed."""
+    monkeypatch.setenv("GB25_GUARD", "1")
+    closure = 0
+    if "=" in variant and variant.startswith("GB25_"):
+        k, v = variant.split("=")
+        monkeypatch.setenv(k, v)
+    elif variant.startswith("closure"):
+        closure = int(variant[-1])
+    m = M.baroclinic_instability_model(M.B200(0), Nx, Ny, Nz, Δt=60.0, grid_type=grid_type,
+                                       physics=PhysicsConfig(closure=closure, kappa=1e-3, nu=1e-2))
+    M.set_baroclinic_instability(m)
+    rng = np.random.default_rng(1)
+    M.set(m, u=1e-3 * rng.random(m.interior("u").shape), v=1e-3 * rng.random(m.interior("v").shape))
+    assert m.handle.check_guards() == 0
+    M.first_time_step(m)
+    M.time_step(m)
+    M.loop(m, 3)
+    for wl in (M.mask_immersed_model_fields_workload, M.tupled_fill_halo_regions_workload, M.compute_auxiliaries_workload,
+               M.compute_tendencies_workload, M.correct_velocities_and_cache_previous_tendencies_workload):
+        wl(m)
+    M.ab2_step_workload(m, 60.0)
+    m.synchronize()
+    assert np.isfinite(m.interior("T")).all() and np.isfinite(m.interior("eta")).all()
+    assert m.handle.check_guards() == 0, "a kernel stored outside its arrays"
+    m.close()
+
+
 def test_baseline_config_c1_latlon_128x64x8_100_steps(oracle_mod):
     """BASELINE.json configs[0]: baroclinic_instability_model on LatitudeLongitudeGrid 128x64x8, Float32,
     1 Euler + 100 AB2 steps, reference state (T = S = 0, random u, v), against the oracle."""
