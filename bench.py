@@ -441,13 +441,15 @@ def main():
                     "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
                     "kernel_ms_per_launch": {k[7:]: v[0] / max(v[1], 1) for k, v in kernels.items()},
                     "exchange_ms_per_step": {k[9:]: v[0] / args.steps for k, v in exch.items()}}
+    field_mb = (Nx + 16) * (Ny + 17) * (Nz + 17) * (8 if FT is np.float64 else 4) / 1e6
+    l2_note = (f"inputs larger than L2: 21 3-D arrays of {field_mb:.0f} MB each are streamed every step (L2 = 126 MB)"
+               if 21 * field_mb > 2 * 126 else "working set fits in L2: latency-bound config")
     line = {"metric": "cell_steps_per_s", "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
             "scaling": args.scaling if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f64" if FT is np.float64 else "f32", "data": "synthetic",
             "config": {"workload": args.workload, "grid": grid_type, "Nx_per_gpu": Nx, "Ny_per_gpu": Ny, "Nz": Nz, "dt": dt,
-                       "partition": [Rx, Ry], "halo": 8, "substeps": 30, "l2": "inputs larger than L2 (each 3-D field is 226 MB)"
-                       if Nx * Ny * Nz * 4 > 126e6 else "working set fits in L2: latency-bound config",
+                       "partition": [Rx, Ry], "halo": 8, "substeps": 30, "l2": l2_note,
                        "state_finite": finite},
             "multi_gpu_bit_identical": bit_identical,
             "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline}

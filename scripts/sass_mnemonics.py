@@ -1,5 +1,5 @@
 """Static SASS instruction mix of the hot kernels (cuobjdump -sass on the in-tree objects; no GPU needed).
-usage: python scripts/sass_mnemonics.py > profiles/sass_r1_v6_mnemonics.md"""
+usage: python scripts/sass_mnemonics.py > profiles/r2/sass_r2_mnemonics.md"""
 import collections
 import os
 import re
@@ -7,10 +7,12 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "gb-25_b200", "csrc")
-KERNELS = [("gb25_tend_tma.o", "k_tracer_tma"), ("gb25_tend_tma.o", "k_mom_tma_p2ILi0"), ("gb25_tend_tma.o", "k_mom_tma_p2ILi1"),
+KERNELS = [("gb25_tend_tma.o", "k_tracer_tmaILb1E"), ("gb25_tend_tma.o", "k_mom_tma_p2ILi0ELb1E"), ("gb25_tend_tma.o", "k_mom_tma_p2ILi1ELb1E"),
+           ("gb25_tend_tma.o", "k_tracer_tmaILb0E"), ("gb25_tend_tma.o", "k_mom_tma_p2ILi0ELb0E"),
            ("gb25_baro.o", "k_baro_persistentILi5ELb0"), ("gb25_baro.o", "k_baro_persistentILi5ELb1"),
            ("gb25_kernels.o", "k_compute_p2"), ("gb25_kernels.o", "k_ab2_uv"), ("gb25_kernels.o", "k_ab2_ts_3d"),
-           ("gb25_kernels.o", "k_correct_3d"), ("gb25_tend_v2.o", "k_aux_columns"), ("gb25_tend_v2.o", "k_generic_list")]
+           ("gb25_kernels.o", "k_correct_3dILb1E"), ("gb25_tend_v2.o", "k_aux_columns_vecILi4E"), ("gb25_tend_v2.o", "k_generic_list"),
+           ("gb25_exchange.o", "k_push_cols_packed"), ("gb25_exchange.o", "k_push_rows")]
 COLS = ["UTMALDG", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "FSEL", "FMNMX", "MUFU", "FCHK", "CALL", "LDS", "LDG", "STG", "LD", "ST", "BAR"]
 
 
