@@ -9,7 +9,8 @@
 // =====================================================================================
 __device__ __forceinline__ void tracer_cell_generic(const DevGrid& g, const real* __restrict__ u, const real* __restrict__ v,
                                                     const real* __restrict__ w, const real* __restrict__ T,
-                                                    const real* __restrict__ S, int i, int j, int k, real& outT, real& outS) {
+                                                    const real* __restrict__ S, int i, int j, int k, real& outT, real& outS,
+                                                    real* ftopT = nullptr, real* ftopS = nullptr) {
   const int q2 = id2(g, i, j), PX = g.PX, n2 = g.n2;
   const size_t q3 = q2 + (size_t)n2 * (k + g.Hz - 1);
   const real eps = g.eps;
@@ -61,6 +62,7 @@ __device__ __forceinline__ void tracer_cell_generic(const DevGrid& g, const real
   const real rV = R(1.) / (az * dz);
   outT = -(rV * dT);
   outS = -(rV * dS);
+  if (ftopT) { *ftopT = fT[1]; *ftopS = fS[1]; }   // (masked) fluxes through the top face, for k-marching callers
 }
 
 // single-tracer variant (same arithmetic) used by the blocked kernel's fallback
@@ -118,10 +120,14 @@ static __device__ __noinline__ real tracer_cell_generic1(const DevGrid* __restri
 // the swapped vorticity is -zeta and WENO reconstruction is odd, so the result is identical.
 // (a, b) below are offsets along the component's own / cross horizontal direction.
 // =====================================================================================
-template <int DIR>
+// SCR: the vorticity and the two flux differences are read from the scratch arrays of k_aux_columns (same expressions,
+// conditional differences included; the swapped vorticity of DIR = 1 is -zeta) instead of being rebuilt from u, v and six
+// metric arrays at each of the 18 stencil points.
+template <int DIR, bool SCR = false>
 __device__ __forceinline__ real momentum_G(const DevGrid& g, const real* __restrict__ own, const real* __restrict__ oth,
                                             const real* __restrict__ w, const real* __restrict__ p, int i, int j, int k,
-                                            real* wtop = nullptr) {
+                                            real* wtop = nullptr, const real* __restrict__ zeta = nullptr,
+                                            const real* __restrict__ dxU = nullptr, const real* __restrict__ dyV = nullptr) {
   const int PX = g.PX, n2 = g.n2;
   const int sO = DIR == 0 ? 1 : PX, sC = DIR == 0 ? PX : 1;
   const real* __restrict__ M1 = DIR == 0 ? g.dxfc : g.dycf;  // own-direction spacing at the own-velocity point
@@ -156,14 +162,19 @@ __device__ __forceinline__ real momentum_G(const DevGrid& g, const real* __restr
 #pragma unroll
   for (int m = 0; m < 6; m++) {
     const int b = m - 2;
-    real d1 = M4[q2 + OF(0, b)] * X[OF(0, b)] - M4[q2 + OF(-1, b)] * X[OF(-1, b)];
-    real d2 = M1[q2 + OF(0, b)] * O[OF(0, b)] - M1[q2 + OF(0, b - 1)] * O[OF(0, b - 1)];
-    if (imm && g.cond_diff) {
-      const bool c00 = inact(0, b, k), c0m = inact(0, b - 1, k), cm0 = inact(-1, b, k), cmm = inact(-1, b - 1, k);
-      if ((c00 && c0m) || (cm0 && cmm)) d1 = R(0.);   // inactive other-velocity nodes
-      if ((c00 && cm0) || (c0m && cmm)) d2 = R(0.);   // inactive own-velocity nodes
+    if (SCR) {
+      const real z = zeta[q3 + OF(0, b)];
+      zq[m] = DIR == 0 ? z : -z;
+    } else {
+      real d1 = M4[q2 + OF(0, b)] * X[OF(0, b)] - M4[q2 + OF(-1, b)] * X[OF(-1, b)];
+      real d2 = M1[q2 + OF(0, b)] * O[OF(0, b)] - M1[q2 + OF(0, b - 1)] * O[OF(0, b - 1)];
+      if (imm && g.cond_diff) {
+        const bool c00 = inact(0, b, k), c0m = inact(0, b - 1, k), cm0 = inact(-1, b, k), cmm = inact(-1, b - 1, k);
+        if ((c00 && c0m) || (cm0 && cmm)) d1 = R(0.);   // inactive other-velocity nodes
+        if ((c00 && cm0) || (c0m && cmm)) d2 = R(0.);   // inactive own-velocity nodes
+      }
+      zq[m] = (d1 - d2) / g.azff[q2 + OF(0, b)];
     }
-    zq[m] = (d1 - d2) / g.azff[q2 + OF(0, b)];
     zs[m] = (O[OF(0, b - 1)] + O[OF(0, b)]) * R(0.5);
     zr[m] = (X[OF(-1, b)] + X[OF(0, b)]) * R(0.5);
   }
@@ -177,8 +188,14 @@ __device__ __forceinline__ real momentum_G(const DevGrid& g, const real* __restr
   for (int m = 0; m < 6; m++) {
     const int a = m - 3;
     const real o0 = O[OF(a, 0)], o1 = O[OF(a + 1, 0)];
-    dOw[m] = M3[q2 + OF(a + 1, 0)] * dz * o1 - M3[q2 + OF(a, 0)] * dz * o0;
-    dOt[m] = M2[q2 + OF(a, 1)] * dz * X[OF(a, 1)] - M2[q2 + OF(a, 0)] * dz * X[OF(a, 0)];
+    if (SCR) {
+      const real fx = dxU[q3 + OF(a, 0)], fy = dyV[q3 + OF(a, 0)];
+      dOw[m] = DIR == 0 ? fx : fy;
+      dOt[m] = DIR == 0 ? fy : fx;
+    } else {
+      dOw[m] = M3[q2 + OF(a + 1, 0)] * dz * o1 - M3[q2 + OF(a, 0)] * dz * o0;
+      dOt[m] = M2[q2 + OF(a, 1)] * dz * X[OF(a, 1)] - M2[q2 + OF(a, 0)] * dz * X[OF(a, 0)];
+    }
     dv[m] = DIR == 0 ? dOw[m] + dOt[m] : dOt[m] + dOw[m];
     dK[m] = o1 * o1 * R(0.5) - o0 * o0 * R(0.5);
     sK[m] = (o0 + o1) * R(0.5);

@@ -684,7 +684,8 @@ __global__ void __launch_bounds__(128, GENERIC_MINB) k_generic_list(DevGrid g, c
                                                       const float* __restrict__ S, float* __restrict__ Gu, float* __restrict__ Gv,
                                                       float* __restrict__ GT, float* __restrict__ GS, float* __restrict__ cu,
                                                       float* __restrict__ cv, float* __restrict__ cT, float* __restrict__ cS,
-                                                      int do_mom, int do_trc) {
+                                                      int do_mom, int do_trc, const float* __restrict__ zeta,
+                                                      const float* __restrict__ dxU, const float* __restrict__ dyV) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= g.nglist) return;
   const int q3 = g.glist[idx];
@@ -693,14 +694,15 @@ __global__ void __launch_bounds__(128, GENERIC_MINB) k_generic_list(DevGrid g, c
   const bool top = (k == (int)g.kgen2[r]) && k < g.Nz;
   if (do_mom) {
     float wu, wv;
-    Gu[q3] = momentum_G<0>(g, u, v, w, p, i, j, k, &wu);
-    Gv[q3] = momentum_G<1>(g, v, u, w, p, i, j, k, &wv);
+    // (zeta, dx(Ax u), dy(Ay v) come from the scratch arrays of the column pass that precedes the tendency kernels)
+    Gu[q3] = momentum_G<0, true>(g, u, v, w, p, i, j, k, &wu, zeta, dxU, dyV);
+    Gv[q3] = momentum_G<1, true>(g, v, u, w, p, i, j, k, &wv, zeta, dxU, dyV);
     if (top) { cu[r] = wu; cv[r] = wv; }
   }
   if (do_trc) {
-    float fT, fS;
-    GT[q3] = tracer_cell_generic1(gp, u, v, w, T, i, j, k, &fT);
-    GS[q3] = tracer_cell_generic1(gp, u, v, w, S, i, j, k, &fS);
+    float fT, fS, gT, gS;
+    tracer_cell_generic(g, u, v, w, T, S, i, j, k, gT, gS, &fT, &fS);   // both tracers share velocities, areas, orders and masks
+    GT[q3] = gT; GS[q3] = gS;
     if (top) { cT[r] = fT; cS[r] = fS; }
   }
 }
@@ -710,6 +712,7 @@ void launch_generic_list(Handle* h, bool momentum, bool tracers) {
   StageScope ts(h, "kernel:k_generic_list");
   k_generic_list<<<(g.nglist + 127) / 128, 128, 0, h->stream>>>(g, h->g_dev, h->f.u, h->f.v, h->f.w, h->f.p, h->f.T, h->f.S,
                                                               h->f.gn[0], h->f.gn[1], h->f.gn[2], h->f.gn[3], h->carry[0],
-                                                              h->carry[1], h->carry[2], h->carry[3], momentum ? 1 : 0, tracers ? 1 : 0);
+                                                              h->carry[1], h->carry[2], h->carry[3], momentum ? 1 : 0, tracers ? 1 : 0,
+                                                              h->zeta, h->dxU, h->dyV);
   h->count_launch();
 }
