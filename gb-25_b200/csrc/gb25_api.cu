@@ -3,6 +3,8 @@
 // (QuasiAdamsBashforth2; SURVEY.md A.4, stage order /root/reference/src/precompile.jl:31-42).
 // There is no CPU path: without a CUDA device gb25_create fails with GB25_ERR_NO_DEVICE.
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -31,6 +33,10 @@ static thread_local std::string g_create_error;
     cudaError_t e0_ = cudaSetDevice((h)->device);                        \
     if (e0_ != cudaSuccess) { (h)->err = cudaGetErrorString(e0_); (h)->sticky = GB25_ERR_CUDA; return GB25_ERR_CUDA; } \
   } while (0)
+
+// Anything that touches the state outside the step path discards what the last step left for the next one: the AB2
+// epilogue's speculation and the "final since" events that let downloads start before the step has finished.
+static inline void invalidate(Handle* h) { h->spec.valid = false; h->early_valid = false; }
 
 static int check_async(Handle* h, const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -251,6 +257,9 @@ extern "C" int gb25_destroy(gb25_handle* h) {
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->stream_d2h) { cudaStreamSynchronize(h->stream_d2h); cudaStreamDestroy(h->stream_d2h); }
+  if (h->ev_ts_final) cudaEventDestroy(h->ev_ts_final);
+  if (h->ev_uv_final) cudaEventDestroy(h->ev_uv_final);
   delete h;
   return GB25_OK;
 }
@@ -301,6 +310,9 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
   CKC(ckcuda(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking), "cudaStreamCreate"));
   CKC(ckcuda(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming), "cudaEventCreate"));
   CKC(ckcuda(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming), "cudaEventCreate"));
+  CKC(ckcuda(cudaStreamCreateWithFlags(&h->stream_d2h, cudaStreamNonBlocking), "cudaStreamCreate"));
+  CKC(ckcuda(cudaEventCreateWithFlags(&h->ev_ts_final, cudaEventDisableTiming), "cudaEventCreate"));
+  CKC(ckcuda(cudaEventCreateWithFlags(&h->ev_uv_final, cudaEventDisableTiming), "cudaEventCreate"));
   CKC(ckcuda(cudaEventCreate(&h->loop_start), "cudaEventCreate"));
   CKC(ckcuda(cudaEventCreate(&h->loop_stop), "cudaEventCreate"));
   DevGrid& g = h->g;
@@ -426,9 +438,24 @@ static int copy_field(Handle* h, int field, real* host, bool to_device, bool int
   const cudaPos dpos = interior ? make_cudaPos((size_t)g.Hx * sizeof(real), g.Hy, three_d ? g.Hz : 0) : make_cudaPos(0, 0, 0);
   if (to_device) { p.srcPtr = hp; p.dstPtr = dp; p.dstPos = dpos; p.kind = cudaMemcpyHostToDevice; }
   else { p.srcPtr = dp; p.srcPos = dpos; p.dstPtr = hp; p.kind = cudaMemcpyDeviceToHost; }
+  // Interior-shaped downloads of the prognostic fields right after a step need not wait for the step's tail: the interiors
+  // of T, S are final once the AB2 stage is done, those of u, v, eta, U, V once the corrector is (the tendency kernels, 70 %
+  // of the step, only read them), so the copy runs on its own stream behind the matching event, under those kernels.
+  if (!to_device && interior && h->early_valid) {
+    cudaEvent_t ev = nullptr;
+    if (field == GB25_T || field == GB25_S) ev = h->ev_ts_final;
+    else if (field == GB25_U || field == GB25_V || field == GB25_ETA || field == GB25_BARO_U || field == GB25_BARO_V) ev = h->ev_uv_final;
+    if (ev) {
+      CK(h, cudaStreamWaitEvent(h->stream_d2h, ev, 0));
+      CK(h, cudaMemcpy3DAsync(&p, h->stream_d2h));
+      h->d2h_pending = true;
+      if (sync) { CK(h, cudaStreamSynchronize(h->stream_d2h)); h->d2h_pending = false; }
+      return GB25_OK;
+    }
+  }
   CK(h, cudaMemcpy3DAsync(&p, h->stream));
   if (to_device) {
-    h->spec.valid = false;
+    invalidate(h);
     // the other half of a double-buffered field receives the same parent, so that halo cells no fill ever writes
     // (y-z corners, the rows behind an impenetrable wall) hold the uploaded values whichever buffer is current
     // (an interior upload touches no halo cell, and the other half's interior is rewritten before it is read)
@@ -475,6 +502,7 @@ extern "C" int gb25_get_fields(gb25_handle* h, int n, const int* fields, real* c
     const int rc = copy_field(h, fields[q], host[q], false, interior != 0, false);
     if (rc != GB25_OK) return rc;
   }
+  if (h->d2h_pending) { CK(h, cudaStreamSynchronize(h->stream_d2h)); h->d2h_pending = false; }
   CK(h, cudaStreamSynchronize(h->stream));
   return GB25_OK;
 }
@@ -490,9 +518,28 @@ extern "C" int gb25_get_clock(const gb25_handle* h, double* time, long* iteratio
   if (last_dt) *last_dt = h->last_dt;
   return GB25_OK;
 }
+// A partitioned handle waits for its neighbours inside the stream (stream memory operations have no time-out of their own):
+// instead of blocking for ever on a neighbour that died, poll the stream and give up after GB25_SYNC_TIMEOUT_S seconds
+// (default 600; 0 = block).
+static int sync_with_timeout(Handle* h) {
+  static const double limit = []() { const char* e = getenv("GB25_SYNC_TIMEOUT_S"); return e ? atof(e) : 600.0; }();
+  if (!h->ex.on || limit <= 0.0) { CK(h, cudaStreamSynchronize(h->stream)); return GB25_OK; }
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    const cudaError_t e = cudaStreamQuery(h->stream);
+    if (e == cudaSuccess) return GB25_OK;
+    if (e != cudaErrorNotReady) { CK(h, e); }
+    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit) {
+      h->err = "gb25_synchronize: timed out waiting for the stream (a neighbouring tile has not arrived)";
+      h->sticky = GB25_ERR_COMM;
+      return GB25_ERR_COMM;
+    }
+    std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
+}
 extern "C" int gb25_synchronize(gb25_handle* h) {
   REQUIRE(h);
-  CK(h, cudaStreamSynchronize(h->stream));
+  { const int rc = sync_with_timeout(h); if (rc != GB25_OK) return rc; }
   if (exchange_check_timeout(h)) { h->err = "halo exchange timed out waiting for a neighbour tile"; h->sticky = GB25_ERR_COMM; return GB25_ERR_COMM; }
   if (baro_check_timeout(h)) { h->err = "split-explicit substeps timed out waiting for a neighbouring band or tile"; h->sticky = GB25_ERR_COMM; return GB25_ERR_COMM; }
   return check_async(h, "gb25_synchronize");
@@ -618,10 +665,12 @@ static void one_time_step_fused(Handle* h, float dt, float chi) {
   h->spec.valid = false;
   if (ts_early) fill_tracers_early(h, zdone_ts);
   if (h->cfg.closure == 2) { StageScope t(h, "vertical_diffusion"); launch_implicit_columns(h, dt, true); }
+  cudaEventRecord(h->ev_ts_final, h->stream);      // the interiors of T, S are final for this step from here on
   { StageScope t(h, "split_explicit_free_surface"); launch_barotropic(h, dt); }
   h->time += (double)dt; h->iteration += 1; h->last_dt = dt;
   bool zdone_uv;
   { StageScope t(h, "correct_velocities_and_cache"); zdone_uv = launch_correct_fused(h); }
+  cudaEventRecord(h->ev_uv_final, h->stream);      // ... and those of u, v, eta, U, V from here on
   // G- <- Gn: swap the buffers; the tendency kernels below overwrite the whole interior of the new Gn,
   // and the halos of both are identically zero
   for (int q = 0; q < 4; q++) {
@@ -642,6 +691,7 @@ static void one_time_step_fused(Handle* h, float dt, float chi) {
   } else {
     stage_tend(h);
   }
+  h->early_valid = true;
 }
 static void one_time_step(Handle* h, float dt, bool euler) {
   euler = euler || (dt != h->last_dt);
@@ -653,12 +703,12 @@ static void one_time_step(Handle* h, float dt, bool euler) {
   stage_update_state(h);
 }
 
-extern "C" int gb25_initialize(gb25_handle* h) { REQUIRE(h); h->spec.valid = false; stage_initialize(h); return check_async(h, "gb25_initialize"); }
-extern "C" int gb25_update_state(gb25_handle* h) { REQUIRE(h); h->spec.valid = false; stage_update_state(h); return check_async(h, "gb25_update_state"); }
+extern "C" int gb25_initialize(gb25_handle* h) { REQUIRE(h); invalidate(h); stage_initialize(h); return check_async(h, "gb25_initialize"); }
+extern "C" int gb25_update_state(gb25_handle* h) { REQUIRE(h); invalidate(h); stage_update_state(h); return check_async(h, "gb25_update_state"); }
 extern "C" int gb25_first_time_step(gb25_handle* h, float dt) {
   REQUIRE(h);
   if (dt <= 0.f) dt = h->last_dt;
-  h->spec.valid = false;
+  invalidate(h);
   stage_initialize(h);
   stage_update_state(h);
   one_time_step(h, dt, true);
@@ -680,25 +730,25 @@ extern "C" int gb25_loop(gb25_handle* h, float dt, int nsteps) {
   h->loop_timed = true;
   return check_async(h, "gb25_loop");
 }
-extern "C" int gb25_mask_immersed_fields(gb25_handle* h) { REQUIRE(h); h->spec.valid = false; stage_mask(h); return check_async(h, "gb25_mask_immersed_fields"); }
-extern "C" int gb25_fill_halo_regions(gb25_handle* h) { REQUIRE(h); h->spec.valid = false; fill_prognostic(h); return check_async(h, "gb25_fill_halo_regions"); }
-extern "C" int gb25_compute_auxiliaries(gb25_handle* h) { REQUIRE(h); h->spec.valid = false; stage_aux(h); return check_async(h, "gb25_compute_auxiliaries"); }
-extern "C" int gb25_compute_tendencies(gb25_handle* h) { REQUIRE(h); h->spec.valid = false; stage_tend(h); return check_async(h, "gb25_compute_tendencies"); }
+extern "C" int gb25_mask_immersed_fields(gb25_handle* h) { REQUIRE(h); invalidate(h); stage_mask(h); return check_async(h, "gb25_mask_immersed_fields"); }
+extern "C" int gb25_fill_halo_regions(gb25_handle* h) { REQUIRE(h); invalidate(h); fill_prognostic(h); return check_async(h, "gb25_fill_halo_regions"); }
+extern "C" int gb25_compute_auxiliaries(gb25_handle* h) { REQUIRE(h); invalidate(h); stage_aux(h); return check_async(h, "gb25_compute_auxiliaries"); }
+extern "C" int gb25_compute_tendencies(gb25_handle* h) { REQUIRE(h); invalidate(h); stage_tend(h); return check_async(h, "gb25_compute_tendencies"); }
 extern "C" int gb25_compute_momentum_tendencies(gb25_handle* h) {
   REQUIRE(h);
-  h->spec.valid = false;
+  invalidate(h);
   { StageScope t(h, "momentum_tendencies"); launch_momentum_tendency(h); }
   return check_async(h, "gb25_compute_momentum_tendencies");
 }
 extern "C" int gb25_compute_tracer_tendencies(gb25_handle* h) {
   REQUIRE(h);
-  h->spec.valid = false;
+  invalidate(h);
   { StageScope t(h, "tracer_tendencies"); launch_tracer_tendency(h); }
   return check_async(h, "gb25_compute_tracer_tendencies");
 }
 extern "C" int gb25_compute_boundary_tendencies(gb25_handle* h) {
   REQUIRE(h);
-  h->spec.valid = false;
+  invalidate(h);
   { StageScope t(h, "boundary_tendencies"); launch_boundary_tendencies(h); }
   return check_async(h, "gb25_compute_boundary_tendencies");
 }
@@ -707,7 +757,7 @@ extern "C" int gb25_set_flux_boundary_condition(gb25_handle* h, int field, int s
   int q = -1;
   if (field == GB25_U) q = 0; else if (field == GB25_V) q = 1; else if (field == GB25_T) q = 2; else if (field == GB25_S) q = 3;
   if (q < 0 || side < 0 || side > 1) { h->err = "gb25_set_flux_boundary_condition: field must be GB25_U/V/T/S, side 0 (bottom) or 1 (top)"; return GB25_ERR_INVALID; }
-  h->spec.valid = false;
+  invalidate(h);
   CK(h, cudaStreamSynchronize(h->stream));
   if (!flux) {
     h->bflux[q][side] = nullptr;      // (the allocation stays in h->allocs until gb25_destroy)
@@ -726,14 +776,14 @@ extern "C" int gb25_set_flux_boundary_condition(gb25_handle* h, int field, int s
 }
 extern "C" int gb25_ab2_step(gb25_handle* h, float dt, float chi) {
   REQUIRE(h);
-  h->spec.valid = false;
+  invalidate(h);
   if (dt <= 0.f) dt = h->last_dt;
   stage_ab2(h, dt, chi);
   return check_async(h, "gb25_ab2_step");
 }
 extern "C" int gb25_correct_velocities_and_cache_previous_tendencies(gb25_handle* h) {
   REQUIRE(h);
-  h->spec.valid = false;
+  invalidate(h);
   stage_correct(h);
   return check_async(h, "gb25_correct_velocities_and_cache_previous_tendencies");
 }

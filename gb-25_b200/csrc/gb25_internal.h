@@ -93,6 +93,10 @@ struct gb25_handle {
   bool use_tma = true;
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // downloads that overlap the tail of a step: copy stream, "interior final since" events of the last fused step
+  cudaStream_t stream_d2h = nullptr;
+  cudaEvent_t ev_ts_final = nullptr, ev_uv_final = nullptr;
+  bool early_valid = false, d2h_pending = false;
   bool use_tma_tracer = true;
   bool use_packed = true;              // FP32x2 (FFMA2) momentum kernels
   void* tma = nullptr;   // TMA tensor maps (gb25_tend_tma.cu)

@@ -99,6 +99,18 @@ def test_interior_and_batched_transfers(oracle_mod, grid_type, Nx, Ny, Nz):
         assert np.array_equal(a, b), n
         want = par.copy(); want[M._interior_slices(rm.grid, M.FIELD_LOC[n])] = a
         assert np.array_equal(rm.parent(n), want), n
+    # right after a step the interior downloads of u, v, T, S, eta, U, V start behind "final since" events, under the
+    # tendency kernels: they must return what the parent-shaped download returns once the step is complete
+    M.sync_states(rm, vm)
+    M.first_time_step(rm)
+    for rep in range(3):
+        M.time_step(rm)
+        prog = ["u", "v", "T", "S", "eta", "U", "V", "w", "Gn_u"]
+        outs = [np.empty(rm.handle.interior_shape(n), dtype=np.float32) for n in prog]
+        rm.handle.get_fields(prog, outs, interior=True)          # no synchronisation in between
+        for n, a in zip(prog, outs):
+            assert np.array_equal(a, rm.parent(n)[M._interior_slices(rm.grid, M.FIELD_LOC[n])]), (rep, n)
+        assert np.array_equal(rm.handle.get_interior("T"), outs[2])
     rm.close()
 
 
