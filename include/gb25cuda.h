@@ -135,7 +135,10 @@ int gb25_interior_shape(const gb25_handle* h, int field, int shape[3]);
 int gb25_set_interior(gb25_handle* h, int field, const gb25_real* host_interior);
 int gb25_get_interior(gb25_handle* h, int field, gb25_real* host_interior);
 /* Batched transfers: n fields, all copies enqueued back to back on the handle's stream (one cudaMemcpy3DAsync per
- * field) and ONE synchronisation at the end.  interior = 0: parent shape, 1: interior shape. */
+ * field) and ONE synchronisation at the end.  interior = 0: parent shape, 1: interior shape.
+ * Interior-shaped downloads of u, v, T, S, eta, U, V issued right after gb25_time_step / gb25_loop do not wait for the
+ * tail of the step: the library knows since which kernel each of these interiors is final (T, S: the AB2 stage; the
+ * others: the corrector) and copies them on a separate stream behind that event, under the tendency kernels. */
 int gb25_set_fields(gb25_handle* h, int n, const int* fields, const gb25_real* const* host, int interior);
 int gb25_get_fields(gb25_handle* h, int n, const int* fields, gb25_real* const* host, int interior);
 /* model.clock: time, iteration, last_Δt (src/baroclinic_instability_model.jl:82) */
