@@ -7,8 +7,8 @@
  *
  * Conventions
  *  - plain C types only; host arrays are borrowed for the duration of the call;
- *  - all arrays are Float32, column-major with x fastest and halos included ("parent" arrays of
- *    Oceananigans fields): a (Tx,Ty,Tz) Julia array is passed as-is;
+ *  - all arrays are gb25_real (Float32 in libgb25cuda.so, Float64 in libgb25cuda_f64.so), column-major with x fastest
+ *    and halos included ("parent" arrays of Oceananigans fields): a (Tx,Ty,Tz) Julia array is passed as-is;
  *  - every function returns 0 on success and a negative gb25_status otherwise; the message of the
  *    last failure is available from gb25_last_error(); no exception crosses the boundary;
  *  - a handle is driven by one thread at a time; compute calls are stream-ordered and asynchronous,
