@@ -4,6 +4,8 @@
 // There is no CPU path: without a CUDA device gb25_create fails with GB25_ERR_NO_DEVICE.
 #include <algorithm>
 #include <chrono>
+#include <mutex>
+#include <vector>
 #include <thread>
 #include <cmath>
 #include <cstdio>
@@ -242,9 +244,36 @@ static int build_immersed_products(Handle* h, const gb25_grid* grid) {
   return GB25_OK;
 }
 
+// A partitioned handle waits for its neighbours inside the stream (stream memory operations have no time-out of their own):
+// instead of blocking for ever on a neighbour that died, poll the stream and give up after GB25_SYNC_TIMEOUT_S seconds
+// (default 600; 0 = block).  Returns cudaErrorNotReady on a time-out.
+static double sync_limit_seconds() { const char* e = getenv("GB25_SYNC_TIMEOUT_S"); return e ? atof(e) : 600.0; }
+static cudaError_t stream_drain(Handle* h, cudaStream_t s) {
+  const double limit = sync_limit_seconds();
+  if (!h->ex.on || limit <= 0.0) return cudaStreamSynchronize(s);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    const cudaError_t e = cudaStreamQuery(s);
+    if (e != cudaErrorNotReady) return e;
+    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit) return cudaErrorNotReady;
+    std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
+}
+
 extern "C" int gb25_destroy(gb25_handle* h) {
   if (!h) return GB25_ERR_INVALID;
   cudaSetDevice(h->device);
+  if (h->stream && h->ex.on) {
+    // a stream that still waits for a neighbour tile would block cudaStreamSynchronize / cudaFree for ever: give up after the
+    // time-out and leave the device memory of this handle to the end of the process
+    bool stuck = stream_drain(h, h->stream) == cudaErrorNotReady;
+    if (!stuck && h->stream2) stuck = stream_drain(h, h->stream2) == cudaErrorNotReady;
+    if (stuck) {
+      fprintf(stderr, "gb25_destroy: a stream of this tile still waits for a neighbour tile; its device memory is not released\n");
+      cudaGetLastError();
+      return GB25_ERR_COMM;
+    }
+  }
   if (h->stream) cudaStreamSynchronize(h->stream);
   exchange_close(h);
   tma_free(h);
@@ -262,6 +291,40 @@ extern "C" int gb25_destroy(gb25_handle* h) {
   if (h->ev_uv_final) cudaEventDestroy(h->ev_uv_final);
   delete h;
   return GB25_OK;
+}
+
+// Lazy module loading (the CUDA 12 default) loads a module / kernel at its first use, and that load may synchronise the
+// context.  A partitioned step enqueues waits for the neighbour tiles; a first use behind such a wait blocks the host until
+// the neighbour has signalled — which never happens when ONE host thread drives all tiles (gb25_exchange_connect_local),
+// because the neighbour's step is enqueued by the same thread afterwards.  So every kernel of the library is loaded on a
+// device when the first handle is created there (cudaFuncGetAttributes is the documented way to preload under the runtime API).
+static int kernel_tables(KernelTable t[5]) {
+  t[0] = kernel_table_core(); t[1] = kernel_table_tend_v2(); t[2] = kernel_table_tend_tma(); t[3] = kernel_table_exchange();
+  t[4] = kernel_table_baro();
+  return 5;
+}
+extern "C" int gb25_kernel_table_size(void) {
+  KernelTable t[5];
+  const int nt = kernel_tables(t);
+  int n = 0;
+  for (int q = 0; q < nt; q++) n += t[q].n;
+  return n;
+}
+static cudaError_t preload_kernels(int device) {
+  static std::mutex mu;
+  static std::vector<int> done;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int d : done) if (d == device) return cudaSuccess;
+  KernelTable t[5];
+  const int nt = kernel_tables(t);
+  for (int q = 0; q < nt; q++)
+    for (int k = 0; k < t[q].n; k++) {
+      cudaFuncAttributes a;
+      const cudaError_t e = cudaFuncGetAttributes(&a, t[q].fn[k]);
+      if (e != cudaSuccess) return e;
+    }
+  done.push_back(device);
+  return cudaSuccess;
 }
 
 extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_handle** out) {
@@ -299,6 +362,11 @@ extern "C" int gb25_create(const gb25_config* cfg, const gb25_grid* grid, gb25_h
   if ((e = cudaSetDevice(h->device)) != cudaSuccess) {
     g_create_error = std::string("gb25_create: cudaSetDevice: ") + cudaGetErrorString(e);
     delete h; return GB25_ERR_NO_DEVICE;
+  }
+  if ((e = preload_kernels(h->device)) != cudaSuccess) {
+    g_create_error = std::string("gb25_create: loading the kernels (is this an sm_100a device?): ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    delete h; return GB25_ERR_CUDA;
   }
 #define CKC(call)                                                                         \
   do { int rc_ = (call); if (rc_ != GB25_OK) { g_create_error = h->err; gb25_destroy(h); return rc_; } } while (0)
@@ -518,24 +586,15 @@ extern "C" int gb25_get_clock(const gb25_handle* h, double* time, long* iteratio
   if (last_dt) *last_dt = h->last_dt;
   return GB25_OK;
 }
-// A partitioned handle waits for its neighbours inside the stream (stream memory operations have no time-out of their own):
-// instead of blocking for ever on a neighbour that died, poll the stream and give up after GB25_SYNC_TIMEOUT_S seconds
-// (default 600; 0 = block).
 static int sync_with_timeout(Handle* h) {
-  static const double limit = []() { const char* e = getenv("GB25_SYNC_TIMEOUT_S"); return e ? atof(e) : 600.0; }();
-  if (!h->ex.on || limit <= 0.0) { CK(h, cudaStreamSynchronize(h->stream)); return GB25_OK; }
-  const auto t0 = std::chrono::steady_clock::now();
-  for (;;) {
-    const cudaError_t e = cudaStreamQuery(h->stream);
-    if (e == cudaSuccess) return GB25_OK;
-    if (e != cudaErrorNotReady) { CK(h, e); }
-    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit) {
-      h->err = "gb25_synchronize: timed out waiting for the stream (a neighbouring tile has not arrived)";
-      h->sticky = GB25_ERR_COMM;
-      return GB25_ERR_COMM;
-    }
-    std::this_thread::sleep_for(std::chrono::microseconds(50));
+  const cudaError_t e = stream_drain(h, h->stream);
+  if (e == cudaErrorNotReady) {
+    h->err = "gb25_synchronize: timed out waiting for the stream (a neighbouring tile has not arrived)";
+    h->sticky = GB25_ERR_COMM;
+    return GB25_ERR_COMM;
   }
+  CK(h, e);
+  return GB25_OK;
 }
 extern "C" int gb25_synchronize(gb25_handle* h) {
   REQUIRE(h);

@@ -452,3 +452,15 @@ bool launch_barotropic_persistent(Handle* h, float dt) {
   P->seq += c.nsubsteps + 1;   // seq0 itself numbers the initial values published in the prologue
   return true;
 }
+
+void baro_plan_prepare(Handle* h) { (void)baro_plan(h); }
+
+// ---------------------------------------------------------------- kernel table (preload_kernels, gb25_api.cu)
+KernelTable kernel_table_baro() {
+  static const void* const k[] = {
+    (const void*)k_baro_persistent<0, false>, (const void*)k_baro_persistent<0, true>, (const void*)k_baro_persistent<2, false>,
+    (const void*)k_baro_persistent<2, true>, (const void*)k_baro_persistent<5, false>, (const void*)k_baro_persistent<5, true>,
+    (const void*)k_baro_persistent<9, false>, (const void*)k_baro_persistent<9, true>,
+  };
+  return {k, (int)(sizeof k / sizeof k[0])};
+}

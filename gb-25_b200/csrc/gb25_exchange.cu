@@ -341,6 +341,7 @@ static int exchange_finish_connect(Handle* h) {
   X.seqs[0] = X.seqs[1] = 0; X.xseqs[0] = X.xseqs[1] = 0; X.lane = 0;
   X.on = true;
   baro_plan_free(h);   // the persistent substep kernel restarts its sequence numbers on the (zeroed) shared flag buffer
+  baro_plan_prepare(h);   // ... and its allocations are made now, not behind the first wait for a neighbour (see preload_kernels)
   return GB25_OK;
 }
 
@@ -492,4 +493,13 @@ void exchange_close(Handle* h) {
   if (h->ex.flags) { cudaFree(h->ex.flags); h->ex.flags = nullptr; }
   if (h->ex.xbox) { cudaFree(h->ex.xbox); h->ex.xbox = nullptr; }
   h->ex.on = false;
+}
+
+// ---------------------------------------------------------------- kernel table (preload_kernels, gb25_api.cu)
+KernelTable kernel_table_exchange() {
+  static const void* const k[] = {
+    (const void*)k_push_rows, (const void*)k_push_cols, (const void*)k_push_cols_packed, (const void*)k_unpack_cols,
+    (const void*)k_push_fold, (const void*)k_signal, (const void*)k_wait,
+  };
+  return {k, (int)(sizeof k / sizeof k[0])};
 }

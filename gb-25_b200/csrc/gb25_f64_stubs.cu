@@ -16,4 +16,8 @@ void tma_free(Handle*) {}
 bool launch_barotropic_persistent(Handle*, float) { return false; }
 void baro_plan_free(Handle*) {}
 int baro_check_timeout(Handle*) { return 0; }
+void baro_plan_prepare(Handle*) {}
+KernelTable kernel_table_tend_v2() { return {nullptr, 0}; }
+KernelTable kernel_table_tend_tma() { return {nullptr, 0}; }
+KernelTable kernel_table_baro() { return {nullptr, 0}; }
 #endif

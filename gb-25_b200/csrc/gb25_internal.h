@@ -167,4 +167,14 @@ void launch_boundary_tendencies(Handle* h);
 void launch_implicit_columns(Handle* h, float dt, bool with_sums);
 bool launch_barotropic_persistent(Handle* h, float dt);   // gb25_baro.cu; false: not applicable, use the substep kernels
 void baro_plan_free(Handle* h);
+void baro_plan_prepare(Handle* h);     // builds the plan of the persistent substep kernel now (allocations, attributes)
 int baro_check_timeout(Handle* h);
+// Every __global__ of a translation unit, for preload_kernels() (gb25_api.cu): lazy module loading (the CUDA 12 default)
+// loads a kernel at its first use and that load may synchronise the context, which must not happen while a stream of the
+// device waits for a neighbour tile.  tests/test_abi.py compares the total with the entry points of the built cubins.
+struct KernelTable { const void* const* fn; int n; };
+KernelTable kernel_table_core();       // gb25_kernels.cu
+KernelTable kernel_table_tend_v2();    // gb25_tend_v2.cu
+KernelTable kernel_table_tend_tma();   // gb25_tend_tma.cu
+KernelTable kernel_table_exchange();   // gb25_exchange.cu
+KernelTable kernel_table_baro();       // gb25_baro.cu

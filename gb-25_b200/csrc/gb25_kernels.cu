@@ -968,3 +968,21 @@ void launch_implicit_columns(Handle* h, float dt, bool with_sums) {
   k_implicit_columns<<<gr, b, 0, h->stream>>>(g, h->f, h->zeta, dt, h->cfg.kappa, h->cfg.nu, h->us2, h->vs2, with_sums ? 1 : 0);
   h->count_launch();
 }
+
+// ---------------------------------------------------------------- kernel table (preload_kernels, gb25_api.cu)
+KernelTable kernel_table_core() {
+  static const void* const k[] = {
+    (const void*)k_halo_south_north, (const void*)k_halo_fold_row, (const void*)k_halo_bottom_top, (const void*)k_halo_periodic_x,
+    (const void*)k_mask_fields, (const void*)k_mask_barotropic, (const void*)k_compute_w, (const void*)k_compute_p,
+    (const void*)k_tracer_tendency, (const void*)k_momentum_tendency<0>, (const void*)k_momentum_tendency<1>,
+    (const void*)k_ab2_columns, (const void*)k_baro_eta, (const void*)k_baro_uv, (const void*)k_baro_finish,
+    (const void*)k_correct_cache, (const void*)k_barotropic_mode, (const void*)k_ab2_fused, (const void*)k_correct_fused,
+    (const void*)k_ab2_uv, (const void*)k_correct_2d, (const void*)k_vdiff_explicit, (const void*)k_boundary_tendencies,
+    (const void*)k_implicit_columns,
+#ifndef GB25_F64
+    (const void*)k_compute_p2, (const void*)k_ab2_ts_3d, (const void*)k_commit_spec, (const void*)k_correct_3d<false>,
+    (const void*)k_correct_3d<true>,
+#endif
+  };
+  return {k, (int)(sizeof k / sizeof k[0])};
+}

@@ -1047,3 +1047,12 @@ void launch_tracer_tendency_tma(Handle* h, const Ab2Spec* spec) {
   else k_tracer_tma<false><<<gr, b, sm, h->stream>>>(g, t->tr[par], tmg, h->f.T, h->f.S, h->f.gn[2], h->f.gn[3], h->carry[2], h->carry[3], ab);
   h->count_launch();
 }
+
+// ---------------------------------------------------------------- kernel table (preload_kernels, gb25_api.cu)
+KernelTable kernel_table_tend_tma() {
+  static const void* const k[] = {
+    (const void*)k_gu_tma, (const void*)k_gv_tma, (const void*)k_mom_tma_p2<0, false>, (const void*)k_mom_tma_p2<0, true>,
+    (const void*)k_mom_tma_p2<1, false>, (const void*)k_mom_tma_p2<1, true>, (const void*)k_tracer_tma<false>, (const void*)k_tracer_tma<true>,
+  };
+  return {k, (int)(sizeof k / sizeof k[0])};
+}

@@ -716,3 +716,12 @@ void launch_generic_list(Handle* h, bool momentum, bool tracers) {
                                                               h->zeta, h->dxU, h->dyV);
   h->count_launch();
 }
+
+// ---------------------------------------------------------------- kernel table (preload_kernels, gb25_api.cu)
+KernelTable kernel_table_tend_v2() {
+  static const void* const k[] = {
+    (const void*)k_tracer_tendency_v2<2>, (const void*)k_aux_columns, (const void*)k_aux_columns_vec<2>, (const void*)k_aux_columns_vec<4>,
+    (const void*)k_gu_v2, (const void*)k_gv_v2, (const void*)k_generic_list,
+  };
+  return {k, (int)(sizeof k / sizeof k[0])};
+}

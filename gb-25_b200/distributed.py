@@ -180,6 +180,50 @@ class LocalPartition:
         self._each(lambda m: m.close())
 
 
+def local_partition_check(devices=(0, 1), grid_type="gaussian_islands", tx=64, ty=48, Nz=10, nsteps=6, log=None):
+    """partition_check for ONE process driving all devices (LocalPartition; the reference's single_gpu_per_process=false,
+    /root/reference/sharding/sharded_baroclinic_instability_simulation_run.jl:49): the run over ``devices`` must equal the
+    single-GPU run of the same global problem bit for bit.  Meant to be the first thing a fresh process does with the
+    library (tests/test_multi_gpu.py runs it in a subprocess): one host thread enqueues the tiles' steps one after the other,
+    so any host-side blocking behind a wait for a neighbour tile — a lazily loaded kernel, an allocation — is a deadlock."""
+    P = LocalPartition(tx, ty, Nz, Δt=60.0, grid_type=grid_type, devices=tuple(devices))
+    gg = P.global_grid
+    rng = np.random.default_rng(42)
+    T, S = _grids.baroclinic_instability_state(gg)
+    ny_v = gg.Ny + (1 if gg.topo_y == _grids.TOPO_BOUNDED else 0)
+    state = {"T": T.astype(np.float32), "S": S.astype(np.float32),
+             "u": (1e-3 * rng.random((Nz, gg.Ny, gg.Nx))).astype(np.float32),
+             "v": (1e-3 * rng.random((Nz, ny_v, gg.Nx))).astype(np.float32)}
+    for n, a in state.items():
+        P.scatter_interior(n, a)
+    P.synchronize()
+    P.first_time_step()
+    P.time_step()
+    P.loop(nsteps - 2)
+    P.synchronize()
+    ref = M.baroclinic_instability_model(M.B200(devices[0]), gg.Nx, gg.Ny, Nz, Δt=60.0, grid_type=grid_type)
+    for n, a in state.items():
+        ref.set_interior(n, a)
+    M.first_time_step(ref)
+    M.time_step(ref)
+    M.loop(ref, nsteps - 2)
+    ok = P.models[0].clock.iteration == ref.clock.iteration == nsteps
+    for n in ("u", "v", "w", "T", "S", "eta", "Gn_u", "Gn_v", "Gn_T", "Gn_S", "Gm_u", "U", "V", "filt_U", "filt_eta"):
+        r, g = ref.interior(n), P.gather_interior(n)
+        g = g[:, :r.shape[1]]
+        r = r[:, :g.shape[1]]
+        if not np.array_equal(r.view(np.uint32), g.view(np.uint32)):
+            ok = False
+            if log:
+                d = np.abs(r.astype(np.float64) - g.astype(np.float64))
+                log(f"MISMATCH {n}: max|d|={np.nanmax(d):.3e} of max {np.abs(r).max():.3e} n={np.count_nonzero(r != g)}")
+    P.close()
+    ref.close()
+    if log:
+        log(f"LOCAL_OK grid={grid_type} devices={tuple(devices)} steps={nsteps}" if ok else "LOCAL_FAIL")
+    return ok
+
+
 def partition_check(dist, local_rank, grid_type="gaussian_islands", tx=64, ty=48, Nz=10, nsteps=5, log=None):
     """The reference's sharded correctness protocol
     (/root/reference/correctness/correctness_sharded_baroclinic_instability_simulation_run.jl: a sharded model against

@@ -47,7 +47,7 @@ EXPORTED_SYMBOLS = (
     "gb25_compute_boundary_tendencies", "gb25_set_flux_boundary_condition",
     "gb25_ab2_step", "gb25_correct_velocities_and_cache_previous_tendencies",
     "gb25_last_loop_seconds", "gb25_kernel_launch_count", "gb25_enable_stage_timers", "gb25_get_stage_times",
-    "gb25_check_guards",
+    "gb25_check_guards", "gb25_kernel_table_size",
     "gb25_exchange_blob_size", "gb25_exchange_export", "gb25_exchange_connect",
     "gb25_exchange_connect_local", "gb25_loop_all",
 )
@@ -123,6 +123,8 @@ def load(float_type=np.float32):
     lib.gb25_last_loop_seconds.argtypes = [H, C.POINTER(C.c_double)]
     lib.gb25_kernel_launch_count.argtypes = [H, C.POINTER(C.c_long)]
     lib.gb25_check_guards.argtypes = [H, C.POINTER(C.c_long)]
+    lib.gb25_kernel_table_size.argtypes = []
+    lib.gb25_kernel_table_size.restype = C.c_int
     lib.gb25_enable_stage_timers.argtypes = [H, C.c_int]
     lib.gb25_get_stage_times.argtypes = [H, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_long), C.c_int]
     lib.gb25_exchange_blob_size.restype = C.c_int

@@ -186,6 +186,11 @@ int gb25_get_stage_times(gb25_handle* h, const char** names, float* ms, long* ca
 /* Debug aid: a handle created while the environment holds GB25_GUARD=1 places every device array between two 64 KiB
  * guard zones; gb25_check_guards counts the guard bytes that kernels have overwritten since (0 = no out-of-bounds store). */
 int gb25_check_guards(gb25_handle* h, long* corrupted_bytes);
+/* Number of CUDA kernels the library holds.  gb25_create loads every one of them on its device up front (lazy module
+ * loading would otherwise load a kernel at its first launch, and that load can block the host behind a stream that waits
+ * for a neighbour tile — a deadlock when one host thread drives all tiles).  No device needed; the test suite compares
+ * the number with the entry points of the built device code. */
+int gb25_kernel_table_size(void);
 
 /* Multi-GPU (one process per GPU).  Neighbour tiles exchange halos over NVLink through peer-mapped
  * memory: every rank exports its exchange window (gb25_exchange_export), the host side gathers the
@@ -200,7 +205,8 @@ int gb25_exchange_connect(gb25_handle* h, const void* blobs, int nranks);
  * r = rx + Rx*ry, each created on its own device (gb25_config.device).  Peer access is enabled between the devices and the
  * neighbours' allocations are used directly (no IPC).  gb25_loop_all enqueues every step on every tile in turn; per-tile
  * calls (gb25_time_step, gb25_first_time_step, ...) must likewise be issued for all tiles before any of them is
- * synchronised. */
+ * synchronised.  Nothing on the step path blocks the host: the kernels are loaded by gb25_create and the allocations of
+ * the persistent substep kernel are made by the connect call. */
 int gb25_exchange_connect_local(gb25_handle** handles, int n);
 int gb25_loop_all(gb25_handle** handles, int n, float dt, int nsteps);
 

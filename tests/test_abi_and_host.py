@@ -37,6 +37,22 @@ def test_library_exports_every_declared_symbol(cuda_lib):
     assert f64.gb25_real_bytes() == 8
 
 
+def test_every_kernel_is_in_the_preload_table(cuda_lib):
+    """gb25_create loads every kernel up front (a lazy load behind a wait for a neighbour tile blocks the host: a deadlock
+    when one host thread drives all tiles).  The tables are hand-written lists: their total must equal the number of
+    kernel entry points in the device code of the built libraries."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    for lib, path in ((cuda_lib, L.LIB_PATH), (L.load(np.float64), L.LIB_PATH_F64)):
+        out = subprocess.run([cuobjdump, "--dump-elf-symbols", path], capture_output=True, text=True, check=True).stdout
+        entries = {ln.split()[-1] for ln in out.splitlines() if "STT_FUNC" in ln and "STO_ENTRY" in ln}
+        assert len(entries) >= 20
+        assert lib.gb25_kernel_table_size() == len(entries), (path, sorted(entries))
+
+
 def test_signatures_carry_no_torch_or_cxx_types():
     hdr = open(os.path.join(ROOT, "include", "gb25cuda.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
