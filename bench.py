@@ -65,14 +65,40 @@ def kernel_source_sha():
     return h.hexdigest()[:16]
 
 
+def kernel_sass_sha(lib_path=None):
+    """sha of the DEVICE code of the built library (cuobjdump -sass, without the lines that carry source paths): what an ncu
+    capture is really a capture of.  A change of host code in a .cu file changes kernel_source_sha but not this."""
+    import hashlib
+    import shutil
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    lib_path = lib_path or os.path.join(ROOT, "gb-25_b200", "csrc", "libgb25cuda.so")
+    if not (os.path.exists(exe) and os.path.exists(lib_path)):
+        return None
+    try:
+        out = subprocess.run([exe, "-sass", lib_path], capture_output=True, text=True, check=True, timeout=300).stdout
+    except Exception:
+        return None
+    h = hashlib.sha256()
+    for ln in out.splitlines():
+        if ln.startswith("identifier") or "/" in ln and ".cu" in ln and "/*" not in ln:
+            continue
+        h.update(ln.encode()); h.update(b"\n")
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic():
+    """Per-kernel DRAM traffic of the last ncu --set full capture, if it was taken on this code: same kernel sources, or —
+    when only host code in those files changed since — the same machine code."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
         return {}, "no capture"
     d = json.load(open(p))
-    if d.get("kernel_source_sha") != kernel_source_sha():
-        return {}, f"stale capture ({d.get('kernel_source_sha')}): kernel sources changed since"
-    return d.get("kernels", {}), d.get("capture", "profiles/ncu_traffic.json")
+    src = d.get("capture", "profiles/ncu_traffic.json")
+    if d.get("kernel_source_sha") == kernel_source_sha():
+        return d.get("kernels", {}), src
+    if d.get("kernel_sass_sha") and d.get("kernel_sass_sha") == kernel_sass_sha():
+        return d.get("kernels", {}), src + f" (device code unchanged since: sass sha {d['kernel_sass_sha']})"
+    return {}, f"stale capture ({d.get('kernel_source_sha')}): kernel sources changed since"
 
 
 def measured_peaks():

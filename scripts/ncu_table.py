@@ -1,5 +1,5 @@
 """Key metrics of an `ncu -i X.ncu-rep --page raw --csv` dump as a markdown table, and (with --traffic OUT.json) the per-kernel
-DRAM traffic file that bench.py reads for `roofline.traffic` (keyed by the sha of the kernel sources it was captured with).
+DRAM traffic file that bench.py reads for `roofline.traffic` (keyed by the sha of the kernel sources and of the device code it was captured with).
 
     ncu -i gpurun_out/prof.ncu-rep --page raw --csv > raw.csv
     python scripts/ncu_table.py raw.csv [--traffic profiles/ncu_traffic.json --capture "<how it was taken>"] > table.md
@@ -59,4 +59,4 @@ if "--traffic" in args:
     for e in kern.values():      # per launch, like roofline.achieved
         e["dram_bytes"] = e["dram_bytes"] / e["launches"]
     kern["__step__"] = {"dram_bytes": step, "launches": len(names)}
-    json.dump({"kernel_source_sha": bench.kernel_source_sha(), "capture": capture, "kernels": kern}, open(out, "w"), indent=1)
+    json.dump({"kernel_source_sha": bench.kernel_source_sha(), "kernel_sass_sha": bench.kernel_sass_sha(), "capture": capture, "kernels": kern}, open(out, "w"), indent=1)
