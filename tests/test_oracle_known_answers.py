@@ -314,3 +314,88 @@ def test_flux_boundary_conditions_known_answer(oracle_mod):
     M.set_flux_boundary_condition(m, "u", "bottom", None)
     M.update_state(m)
     assert not m.interior("Gn_T").any() and not m.interior("Gn_u").any()
+
+
+def test_weno5_converges_at_fifth_order(small64):
+    """Cell averages of sin(x): the reconstructed face value converges like h^5 on smooth data (both biases)."""
+    xf = 1.0                                                       # the face, fixed while the cells shrink around it
+    errs = {True: [], False: []}
+    for h in (0.2, 0.1, 0.05):
+        edges = xf + h * (np.arange(7) - 3)
+        q = (np.cos(edges[:-1]) - np.cos(edges[1:])) / h           # exact cell averages
+        for left in (True, False):
+            errs[left].append(abs(small64.weno(3, left, q) - np.sin(xf)))
+    for left in (True, False):
+        e = errs[left]
+        assert e[0] > e[1] > e[2] > 0
+        for a, b in zip(e[:-1], e[1:]):
+            assert 4.5 < np.log2(a / b) < 5.7, (left, e)
+
+
+@pytest.mark.parametrize("grid_type", ["simple_lat_lon", "gaussian_islands"])
+def test_uniform_tracers_stay_uniform(oracle_mod, grid_type):
+    """Constancy preservation of the flux-form tracer advection (rows A3 + A6): with w diagnosed from continuity, a uniform
+    T, S has zero tendency for ANY masked velocity field, immersed boundaries and the fold included."""
+    m = M.baroclinic_instability_model(oracle_mod.CPUOracle(np.float64), 48, 24, 8, Δt=30.0, grid_type=grid_type,
+                                       model_cls=oracle_mod.OracleModel)
+    rng = np.random.default_rng(3)
+    U0 = 0.5
+    M.set(m, T=12.5 + 0 * m.interior("T"), S=35.0 + 0 * m.interior("S"),
+          u=U0 * (rng.random(m.interior("u").shape) - 0.5), v=U0 * (rng.random(m.interior("v").shape) - 0.5))
+    M.update_state(m)
+    g = m.grid
+    dx = min(float(np.min(g.metrics[k][g.Hy:g.Hy + g.Ny, g.Hx:g.Hx + g.Nx])) for k in ("dx_cc", "dy_cc"))
+    assert np.abs(m.interior("w")).max() > 0
+    for n, c in (("Gn_T", 12.5), ("Gn_S", 35.0)):
+        scale = c * U0 / dx                                          # size of one flux-difference term
+        assert np.abs(m.interior(n)).max() < 1e-11 * scale, n
+
+
+def test_coriolis_sign_and_magnitude(oracle_mod):
+    """Rows A5 / U-decisions on the Coriolis term: for a vanishingly small uniform flow (advection is quadratic and drops
+    out), horizontally uniform T, S and eta = 0, the momentum tendencies are Gu = +f v, Gv = -f u with f = 2 Omega sin(phi)."""
+    g = grids.simple_latitude_longitude_grid(16, 96, 6)     # 1.7 degrees in latitude: the y-averages of f are exact to 2e-4
+    m = oracle_mod.OracleModel(oracle_mod.CPUOracle(np.float64), g)
+    U0, V0 = 1e-8, -2e-8
+    M.set(m, T=10.0 + 0 * m.interior("T"), S=35.0 + 0 * m.interior("S"),
+          u=U0 + 0 * m.interior("u"), v=V0 + 0 * m.interior("v"))
+    M.update_state(m)
+    Omega = 7.292115e-5
+    phi_c = np.deg2rad(g.phi_cc[g.Hy:g.Hy + g.Ny, g.Hx])            # latitude of cell centres, one per row
+    f_c = 2 * Omega * np.sin(phi_c)
+    Gu, Gv = m.interior("Gn_u"), m.interior("Gn_v")
+    js = slice(3, g.Ny - 3)                                           # away from the walls (v = 0 there)
+    fu = f_c[js][None, :, None]
+    assert np.abs(Gu[:, js] - fu * V0).max() < 1e-3 * np.abs(fu * V0).max()
+    # v row r sits on the face between the centres of rows r-1 and r: f there is their mean to O(dphi^2)
+    f_f = 0.5 * (f_c[2:g.Ny - 4] + f_c[3:g.Ny - 3])[None, :, None]
+    assert np.abs(Gv[:, js] + f_f * U0).max() < 1e-3 * np.abs(f_f * U0).max()
+
+
+def test_surface_pressure_gradient_accelerates_the_flow_by_g_grad_eta_dt(oracle_mod):
+    """Rows A10 + A11 against an analytic answer: from rest, with uniform T, S and a small free-surface displacement
+    eta = A sin(lambda), one step that is short against the gravity-wave period leaves u = -g (d eta/dx) tbar and v ~ 0, where
+    tbar = dt * sum_m w_m m (2/30) = 1.00925 dt is the mean time of the averaging weights of the split-explicit substeps."""
+    from gb25_b200.config import PhysicsConfig
+    g = grids.simple_latitude_longitude_grid(64, 32, 4)
+    dt, A = 1.0, 1e-3
+    m = M.baroclinic_instability_model(oracle_mod.CPUOracle(np.float64), 64, 32, 4, Δt=dt, grid_type="simple_lat_lon",
+                                       model_cls=oracle_mod.OracleModel)
+    g = m.grid
+    lam_c = np.deg2rad(g.lam_cc[g.Hy:g.Hy + g.Ny, g.Hx:g.Hx + g.Nx])
+    phi_c = np.deg2rad(g.phi_cc[g.Hy:g.Hy + g.Ny, g.Hx:g.Hx + g.Nx])
+    M.set(m, T=10.0 + 0 * m.interior("T"), S=35.0 + 0 * m.interior("S"), u=0 * m.interior("u"), v=0 * m.interior("v"),
+          eta=(A * np.sin(lam_c))[None])
+    M.first_time_step(m)
+    dlam = 2 * np.pi / g.Nx
+    lam_f = lam_c - 0.5 * dlam                                         # u points: west faces of the cells
+    # centred difference of sin over dlam = cos(lam_f) * sin(dlam/2) / (dlam/2): use the discrete derivative, exact for the scheme
+    deta_dx = A * np.cos(lam_f) * np.sin(0.5 * dlam) / (0.5 * dlam) / (grids.R_EARTH * np.cos(phi_c))
+    frac, w = averaging_weights(30)
+    tbar = dt * frac * float((w * np.arange(1, len(w) + 1)).sum())
+    assert abs(tbar / dt - 1.0) < 0.02
+    u_expected = -PhysicsConfig().g * deta_dx * tbar
+    u = m.interior("u")
+    for k in range(g.Nz):
+        assert np.abs(u[k] - u_expected).max() < 1e-6 * np.abs(u_expected).max()
+    assert np.abs(m.interior("v")).max() < 1e-3 * np.abs(u_expected).max()
