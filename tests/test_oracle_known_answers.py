@@ -399,3 +399,35 @@ def test_surface_pressure_gradient_accelerates_the_flow_by_g_grad_eta_dt(oracle_
     for k in range(g.Nz):
         assert np.abs(u[k] - u_expected).max() < 1e-6 * np.abs(u_expected).max()
     assert np.abs(m.interior("v")).max() < 1e-3 * np.abs(u_expected).max()
+
+
+def test_baroclinic_pressure_gradient_from_a_numpy_restatement(oracle_mod):
+    """Rows A4 + A5 (pressure part): at rest with T = T0 + a sin(lambda), Gu is minus the zonal difference of the hydrostatic
+    pressure anomaly, p(k) = p(k+1) - (b(k) + b(k+1))/2 (z_c(k+1) - z_c(k)) from the surface down (b = -g rho'/rho0, the level
+    above the surface being the mirror halo).  Restated here in NumPy from the density accessor alone; a warm (light) column
+    to the east pulls the deep flow eastwards."""
+    from gb25_b200.config import PhysicsConfig
+    m = M.baroclinic_instability_model(oracle_mod.CPUOracle(np.float64), 32, 16, 6, Δt=1.0, grid_type="simple_lat_lon",
+                                       model_cls=oracle_mod.OracleModel)
+    g, ph = m.grid, PhysicsConfig()
+    lam_c = np.deg2rad(g.lam_cc[g.Hy, g.Hx:g.Hx + g.Nx])
+    Tcol = 10.0 + 0.5 * np.sin(lam_c)
+    M.set(m, T=Tcol[None, None, :] + 0 * m.interior("T"), S=35.0 + 0 * m.interior("S"), u=0 * m.interior("u"), v=0 * m.interior("v"))
+    M.update_state(m)
+    f32 = lambda a: np.asarray(a, dtype=np.float32).astype(np.float64)    # the model holds Float32 grid products
+    zc = f32(g.z["z_c"])[g.Hz:g.Hz + g.Nz + 1]                           # centres 1..Nz and the first halo centre above
+    dzf = f32(g.z["dz_f"])[g.Hz + 1:g.Hz + g.Nz + 1]                     # spacing between centres k and k+1
+    grav, rho0 = float(np.float32(ph.g)), float(np.float32(ph.rho0))     # (the configuration struct carries floats)
+    b = np.array([[-grav * m.rho_prime(float(T), 35.0, float(z)) / rho0 for T in Tcol] for z in zc])   # (Nz+1, Nx)
+    p = np.zeros((g.Nz, g.Nx))
+    acc = np.zeros(g.Nx)
+    for k in range(g.Nz - 1, -1, -1):
+        acc = acc - 0.5 * (b[k] + b[k + 1]) * dzf[k]
+        p[k] = acc
+    dx = f32(g.metrics["dx_fc"])[g.Hy:g.Hy + g.Ny, g.Hx:g.Hx + g.Nx]      # at the u points
+    expected = -(p[:, None, :] - np.roll(p, 1, axis=1)[:, None, :]) / dx[None]
+    Gu = m.interior("Gn_u")
+    assert np.abs(Gu - expected).max() < 1e-10 * np.abs(expected).max()
+    assert np.abs(m.interior("p")[:, 3, :] - p).max() < 1e-12 * np.abs(p).max()
+    i_east_warm = int(np.argmax(np.cos(lam_c - 0.5 * (lam_c[1] - lam_c[0]))))   # u point where dT/dx is largest
+    assert Gu[0, g.Ny // 2, i_east_warm] > 0
