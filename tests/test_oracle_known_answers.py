@@ -431,3 +431,63 @@ def test_baroclinic_pressure_gradient_from_a_numpy_restatement(oracle_mod):
     assert np.abs(m.interior("p")[:, 3, :] - p).max() < 1e-12 * np.abs(p).max()
     i_east_warm = int(np.argmax(np.cos(lam_c - 0.5 * (lam_c[1] - lam_c[0]))))   # u point where dT/dx is largest
     assert Gu[0, g.Ny // 2, i_east_warm] > 0
+
+
+def test_solid_body_rotation_gives_the_centripetal_and_coriolis_terms(oracle_mod):
+    """Row A5, the nonlinear part: for u = U0 cos(phi), v = 0 (solid-body rotation; no dependence on longitude, w = 0) the
+    vector-invariant tendency is Gu = 0 and Gv = -f u - u^2 tan(phi) / R: the relative vorticity 2 U0 sin(phi) / R times u
+    plus the kinetic-energy gradient make exactly the metric term of the sphere.  The part even in U0 isolates it from the
+    Coriolis part (odd); both converge to the analytic values at second order in the latitude spacing."""
+    U0 = 10.0
+    err = {}
+    for Ny in (48, 96):
+        Gv = {}
+        for sgn in (1.0, -1.0):
+            m = M.baroclinic_instability_model(oracle_mod.CPUOracle(np.float64), 16, Ny, 4, Δt=1.0, grid_type="simple_lat_lon",
+                                               model_cls=oracle_mod.OracleModel)
+            g = m.grid
+            phi_c = np.deg2rad(g.phi_cc[g.Hy:g.Hy + g.Ny, g.Hx])
+            M.set(m, T=10.0 + 0 * m.interior("T"), S=35.0 + 0 * m.interior("S"),
+                  u=sgn * U0 * np.cos(phi_c)[None, :, None] + 0 * m.interior("u"), v=0 * m.interior("v"))
+            M.update_state(m)
+            assert np.abs(m.interior("Gn_u")).max() == 0.0 and np.abs(m.interior("w")).max() == 0.0
+            Gv[sgn] = m.interior("Gn_v")[0, 1:Ny, 0]                    # v rows 1 .. Ny-1 (between the centres r-1 and r)
+        phi_f = 0.5 * (phi_c[:-1] + phi_c[1:])
+        u_f = U0 * np.cos(phi_f)
+        js = slice(6, Ny - 7)                                           # away from the walls
+        metric = 0.5 * (Gv[1.0] + Gv[-1.0])[js]
+        coriolis = 0.5 * (Gv[1.0] - Gv[-1.0])[js]
+        exp_metric = (-u_f ** 2 * np.tan(phi_f) / grids.R_EARTH)[js]
+        exp_coriolis = (-2 * grids.OMEGA_EARTH * np.sin(phi_f) * u_f)[js]
+        err[Ny] = (np.abs(metric - exp_metric).max() / np.abs(exp_metric).max(),
+                   np.abs(coriolis - exp_coriolis).max() / np.abs(exp_coriolis).max())
+    assert err[48][0] < 2e-3 and err[48][1] < 1e-3
+    for q in (0, 1):
+        assert 3.0 < err[48][q] / err[96][q] < 5.0, err                # second order
+
+
+def test_tracer_advection_by_solid_body_rotation(oracle_mod):
+    """Row A6 against an analytic answer: solid-body rotation with angular velocity U0/R carries T = T0 + a sin(lambda)
+    around the axis, dT/dt = -(U0/R) a cos(lambda) at every latitude and depth.  Point values of sin at the cell centres are
+    the cell averages of a rescaled sine whose averaged derivative is a cos(lambda_c) again, so the only differences are the
+    finite-volume factor dphi / (2 sin(dphi/2)) of the exact spherical cell areas and the truncation error of the WENO5
+    reconstruction — which must fall like dlambda^5."""
+    U0, a = 10.0, 0.5
+    err = {}
+    for Nx in (32, 64):
+        m = M.baroclinic_instability_model(oracle_mod.CPUOracle(np.float64), Nx, 24, 4, Δt=1.0, grid_type="simple_lat_lon",
+                                           model_cls=oracle_mod.OracleModel)
+        g = m.grid
+        phi_c = np.deg2rad(g.phi_cc[g.Hy:g.Hy + g.Ny, g.Hx])
+        lam_c = np.deg2rad(g.lam_cc[g.Hy, g.Hx:g.Hx + g.Nx])
+        dphi = phi_c[1] - phi_c[0]
+        for sgn in (1.0, -1.0):                                         # both upwind directions
+            M.set(m, T=10.0 + a * np.sin(lam_c)[None, None, :] + 0 * m.interior("T"), S=35.0 + 0 * m.interior("S"),
+                  u=sgn * U0 * np.cos(phi_c)[None, :, None] + 0 * m.interior("u"), v=0 * m.interior("v"))
+            M.update_state(m)
+            expected = -sgn * (U0 / grids.R_EARTH) * a * np.cos(lam_c) * dphi / (2 * np.sin(dphi / 2))
+            err[Nx, sgn] = np.abs(m.interior("Gn_T") - expected[None, None, :]).max() / np.abs(expected).max()
+            assert np.abs(m.interior("Gn_S")).max() < 1e-12 * 35.0 * U0 / grids.R_EARTH
+    for sgn in (1.0, -1.0):
+        assert err[32, sgn] < 1e-5 and err[64, sgn] < 3e-7, err
+        assert 20.0 < err[32, sgn] / err[64, sgn] < 45.0, err         # fifth order
