@@ -715,3 +715,16 @@ def test_dump_and_resume_is_bit_exact(tmp_path, oracle_mod):
     assert rm2.clock.iteration == rm.clock.iteration == 6
     for n in ("u", "v", "w", "T", "S", "eta", "Gn_u", "Gn_T", "Gm_u", "U", "filt_U"):
         assert np.array_equal(rm.parent(n).view(np.uint32), rm2.parent(n).view(np.uint32)), n
+
+
+def test_analytic_answers_on_the_device():
+    """No oracle in this one: libgb25cuda against analytic answers (tests/analytic_answers.py) — Coriolis sign and magnitude,
+    u = -g d(eta)/dx tbar after one short step from a free-surface slope, the centripetal term -u^2 tan(phi)/R of solid-body
+    rotation, the advection of a sine of temperature by that rotation, and constancy preservation over the islands and the
+    fold.  The thresholds are Float32 ones; the Float32 oracle meets each at a third (CPU test of the same name)."""
+    import analytic_answers as AA
+    mk = lambda Nx, Ny, Nz, dt, gt: M.baroclinic_instability_model(M.B200(0), Nx, Ny, Nz, Δt=dt, grid_type=gt)
+    err = AA.analytic_errors(mk)
+    assert set(err) == set(AA.THRESHOLDS)
+    bad = {k: (v, AA.THRESHOLDS[k]) for k, v in err.items() if not (np.isfinite(v) and v <= AA.THRESHOLDS[k])}
+    assert not bad, bad

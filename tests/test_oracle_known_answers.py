@@ -491,3 +491,15 @@ def test_tracer_advection_by_solid_body_rotation(oracle_mod):
     for sgn in (1.0, -1.0):
         assert err[32, sgn] < 1e-5 and err[64, sgn] < 3e-7, err
         assert 20.0 < err[32, sgn] / err[64, sgn] < 45.0, err         # fifth order
+
+
+def test_float32_oracle_meets_the_analytic_answers_the_device_is_held_to(oracle_mod):
+    """tests/analytic_answers.py with the Float32 oracle in the model seat: every check at no more than a third of the
+    threshold that tests/test_cuda_parity.py::test_analytic_answers_on_the_device applies to libgb25cuda."""
+    import analytic_answers as AA
+    mk = lambda Nx, Ny, Nz, dt, gt: M.baroclinic_instability_model(oracle_mod.CPUOracle(np.float32), Nx, Ny, Nz, Δt=dt,
+                                                                    grid_type=gt, model_cls=oracle_mod.OracleModel)
+    err = AA.analytic_errors(mk)
+    assert set(err) == set(AA.THRESHOLDS)
+    for k, v in err.items():
+        assert np.isfinite(v) and v <= AA.THRESHOLDS[k] / 3, (k, v, AA.THRESHOLDS[k])
