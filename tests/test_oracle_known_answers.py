@@ -530,3 +530,53 @@ def test_time_loop_translates_a_tracer_wave_like_the_analytic_solution(oracle_mo
     assert np.abs(m.interior("T") - exact[None, None, :]).max() < 1e-4 * change
     assert np.abs(m.interior("u") - u0).max() < 1e-5 * U0                 # the rotation stayed steady
     assert np.abs(m.interior("S") - 35.0).max() < 1e-12
+
+
+def test_fold_index_maps_agree_with_the_geometry_of_the_tripolar_map():
+    """The zipper maps (grids.fold_index_maps; decision U1: Centre row Ny lies on the fold line) against geometry, with no
+    reference to the fill code: the conformal map z = Z + a^2/Z sends (Lambda, R) and (-Lambda, a^2/R) to the same point of the
+    sphere, so the halo cell (i, Ny+m) IS the interior cell at longitude index i' with -Lambda_i = Lambda_i' (exactly) and at
+    the row whose logical latitude mirrors Phi_N + m dPhi (to second order in m dPhi).  For all four staggerings the mapped
+    source cell is within a quarter of a cell of the analytic continuation in the first halo row, and every off-by-one
+    alternative is at least three quarters of a cell away, in every column."""
+    Nx, Ny, Hx, Hy = 256, 128, 8, 8
+    north, south, first = 55.0, -80.0, 70.0
+    a = 0.5 * np.tan(np.deg2rad(90.0 - north) / 2)
+    Phi_N = 90.0 - 2 * np.rad2deg(np.arctan(a))
+    dPhi, dLam = (Phi_N - south) / (Ny - 0.5), 360.0 / Nx
+    j = np.arange(1 - Hy, Ny + Hy + 2, dtype=np.float64)
+    i = np.arange(1 - Hx, Nx + Hx + 1, dtype=np.float64)
+    Phif = south + (j - 1) * dPhi
+    Lamf = (i - 1) * dLam
+    logical = {"cc": (Lamf + dLam / 2, Phif + dPhi / 2), "fc": (Lamf, Phif + dPhi / 2), "cf": (Lamf + dLam / 2, Phif), "ff": (Lamf, Phif)}
+
+    def geographic(Lam, Phi):
+        L, P = np.meshgrid(np.deg2rad(Lam), Phi)
+        Z = np.tan(np.deg2rad(90.0 - P) / 2) * np.exp(1j * L)
+        zz = Z + a * a / Z
+        return np.mod(np.rad2deg(np.angle(zz)) + first, 360.0), 90.0 - 2 * np.rad2deg(np.arctan(np.abs(zz)))
+
+    def dist(l1, p1, l2, p2):
+        l1, p1, l2, p2 = (np.deg2rad(x) for x in (l1, p1, l2, p2))
+        return np.rad2deg(np.arccos(np.clip(np.sin(p1) * np.sin(p2) + np.cos(p1) * np.cos(p2) * np.cos(l1 - l2), -1, 1)))
+
+    lam_all = (np.arange(1, Nx + 1) - 0.5) * dLam
+    cols = np.arange(1, Nx + 1)[np.minimum(lam_all % 180, 180 - lam_all % 180) > 25]     # away from the two grid poles
+    for tag, (lx, ly) in {"cc": (0, 0), "fc": (1, 0), "cf": (0, 1), "ff": (1, 1)}.items():
+        Lam, Phi = logical[tag]
+        isrc, quirk, jsrc = grids.fold_index_maps(Nx, Ny, Hx, Hy, lx, ly)
+        # longitudes: -Lambda_i = Lambda_i' exactly (mod 360), the wrap of the Face-x map included
+        lam_i, lam_src = Lam[np.arange(1, Nx + 1) + Hx - 1], Lam[isrc + Hx - 1]
+        assert np.abs(np.mod(-lam_i - lam_src + 180.0, 360.0) - 180.0).max() < 1e-9
+        assert quirk.sum() == (1 if lx else 0)
+        lam, phi = geographic(Lam, Phi)
+        jh = Ny + 1 + Hy - 1                                               # first halo row
+        for name, (di, dj) in {"map": (0, 0), "i+1": (1, 0), "i-1": (-1, 0), "j+1": (0, 1), "j-1": (0, -1)}.items():
+            ii = ((isrc[cols - 1] + di - 1) % Nx) + 1
+            jj = jsrc[0] + dj
+            d = dist(lam[jh, cols + Hx - 1], phi[jh, cols + Hx - 1], lam[jj + Hy - 1, ii + Hx - 1], phi[jj + Hy - 1, ii + Hx - 1])
+            cell = dist(lam[jj + Hy - 1, ii + Hx - 1], phi[jj + Hy - 1, ii + Hx - 1], lam[jj + Hy - 1, ii + Hx], phi[jj + Hy - 1, ii + Hx])
+            if name == "map":
+                assert (d / cell).max() < 0.25, (tag, float((d / cell).max()))
+            else:
+                assert (d / cell).min() > 0.75, (tag, name, float((d / cell).min()))
