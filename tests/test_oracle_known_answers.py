@@ -578,5 +578,16 @@ def test_fold_index_maps_agree_with_the_geometry_of_the_tripolar_map():
             cell = dist(lam[jj + Hy - 1, ii + Hx - 1], phi[jj + Hy - 1, ii + Hx - 1], lam[jj + Hy - 1, ii + Hx], phi[jj + Hy - 1, ii + Hx])
             if name == "map":
                 assert (d / cell).max() < 0.25, (tag, float((d / cell).max()))
+                # both grid directions are reversed at the mirror cell: vector components change sign under the fold
+                # (the -1 that the u, v, U, V fills carry), scalars do not
+                xyz = lambda J, I: np.stack([np.cos(np.deg2rad(phi[J, I])) * np.cos(np.deg2rad(lam[J, I])),
+                                             np.cos(np.deg2rad(phi[J, I])) * np.sin(np.deg2rad(lam[J, I])),
+                                             np.sin(np.deg2rad(phi[J, I]))])
+                unit = lambda v: v / np.linalg.norm(v, axis=0)
+                Ih, Is, Js = cols + Hx - 1, ii + Hx - 1, jj + Hy - 1
+                for dJ, dI in ((0, 1), (1, 0)):
+                    e_halo = unit(xyz(jh + dJ, Ih + dI) - xyz(jh, Ih))
+                    e_src = unit(xyz(Js + dJ, Is + dI) - xyz(Js, Is))
+                    assert (e_halo * e_src).sum(axis=0).max() < -0.95, (tag, dJ, dI)
             else:
                 assert (d / cell).min() > 0.75, (tag, name, float((d / cell).min()))
