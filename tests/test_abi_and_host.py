@@ -53,6 +53,38 @@ def test_every_kernel_is_in_the_preload_table(cuda_lib):
         assert lib.gb25_kernel_table_size() == len(entries), (path, sorted(entries))
 
 
+def test_header_is_plain_c_and_the_c_example_builds_its_grid_like_the_host_mirror(tmp_path, cuda_lib):
+    """include/gb25cuda.h compiles as C99 (-pedantic), examples/lat_lon_from_c.c links against the library with gcc alone, its
+    grid products equal those of gb25_b200.grids (checksums), and without a device it fails loudly with GB25_ERR_NO_DEVICE."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    src = os.path.join(ROOT, "examples", "lat_lon_from_c.c")
+    libdir = os.path.dirname(L.LIB_PATH)
+    exe = str(tmp_path / "lat_lon_from_c")
+    for flags, lib in (([], "gb25cuda"), (["-DGB25_F64"], "gb25cuda_f64")):
+        r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-O1", *flags, "-I", os.path.join(ROOT, "include"),
+                            src, "-o", exe + lib, "-L", libdir, "-l" + lib, "-lm"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    env = dict(os.environ, LD_LIBRARY_PATH=libdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    out = subprocess.run([exe + "gb25cuda", "--checksums"], capture_output=True, text=True, env=env, check=True).stdout
+    got = dict(ln.split() for ln in out.strip().splitlines())
+    g = grids.simple_latitude_longitude_grid(64, 32, 8)
+    f32 = lambda a: np.abs(np.asarray(a, dtype=np.float32).astype(np.float64)).sum()
+    for k in ("dx_cc", "dx_cf", "dy_cc", "az_cc", "az_cf", "f_ff"):
+        assert float(got[k]) == pytest.approx(f32(g.metrics[k]), rel=1e-7), k
+    for k in ("z_f", "z_c", "dz_c", "dz_f"):
+        assert float(got[k]) == pytest.approx(f32(g.z[k]), rel=1e-7), k
+    from gb25_b200.splitexplicit import averaging_weights
+    _, w = averaging_weights(30)
+    assert int(got["nweights"]) == len(w) and float(got["weights"]) == pytest.approx(f32(w), rel=1e-7)
+    if not _has_gpu():
+        r = subprocess.run([exe + "gb25cuda"], capture_output=True, text=True, env=env)
+        assert r.returncode == 2 and "no CPU path" in r.stderr, (r.returncode, r.stderr)
+
+
 def test_signatures_carry_no_torch_or_cxx_types():
     hdr = open(os.path.join(ROOT, "include", "gb25cuda.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
