@@ -728,3 +728,36 @@ def test_analytic_answers_on_the_device():
     assert set(err) == set(AA.THRESHOLDS)
     bad = {k: (v, AA.THRESHOLDS[k]) for k, v in err.items() if not (np.isfinite(v) and v <= AA.THRESHOLDS[k])}
     assert not bad, bad
+
+
+_FIRST_RUN = "first run on a GPU is the round-end suite: the round-2 GPU budget was spent before this test existed (XPASS = it works)"
+
+
+@pytest.mark.xfail(strict=False, reason=_FIRST_RUN)
+def test_analytic_answers_on_the_device_float64_build():
+    """The Float64 build (libgb25cuda_f64.so, operator-per-kernel generation) against the same analytic answers."""
+    import analytic_answers as AA
+    mk = lambda Nx, Ny, Nz, dt, gt: M.baroclinic_instability_model(M.B200(0), Nx, Ny, Nz, Δt=dt, grid_type=gt, float_type=np.float64)
+    err = AA.analytic_errors(mk)
+    bad = {k: (v, AA.THRESHOLDS[k]) for k, v in err.items() if not (np.isfinite(v) and v <= AA.THRESHOLDS[k])}
+    assert not bad, bad
+
+
+@pytest.mark.xfail(strict=False, reason=_FIRST_RUN)
+def test_c_example_runs_on_the_device(tmp_path):
+    """examples/lat_lon_from_c.c, compiled with gcc against the header alone, steps the model 11 times on the device."""
+    import os
+    import shutil
+    import subprocess
+    from gb25_b200 import lib as L
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    libdir = os.path.dirname(L.LIB_PATH)
+    exe = str(tmp_path / "lat_lon_from_c")
+    subprocess.run([gcc, "-std=c99", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "lat_lon_from_c.c"),
+                    "-o", exe, "-L", libdir, "-lgb25cuda", "-lm"], check=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=libdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and "iteration 11" in r.stdout and "all finite" in r.stdout, r.stdout + r.stderr
